@@ -1,0 +1,170 @@
+/*
+ * phyloligo_b200 -- C ABI of the B200-native PhylOligo hot path.
+ *
+ * The reference (itsmeludo/PhylOligo) is pure Python: it has no FFI layer.  The
+ * seam this library sits behind is the set of worker functions that the
+ * reference's scoop / joblib back-ends call.  Each entry
+ * point below names the reference worker(s) it replaces, with file:line into
+ * /root/reference/phylopackage.  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types.
+ *   - every function returns 0 (PO_OK) or a negative po_status; the message of
+ *     the last failure on the calling thread is available from po_last_error().
+ *   - pointers named d_* are DEVICE pointers on the current CUDA device, owned
+ *     and allocated by the caller (the Python host uses torch for that).
+ *     Pointers named h_* are host pointers.
+ *   - `stream` is a cudaStream_t passed as void*; all device work is enqueued
+ *     on it and nothing synchronises unless stated.
+ */
+#ifndef PHYLOLIGO_B200_H
+#define PHYLOLIGO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* po_stream_t; /* cudaStream_t */
+
+enum po_status {
+    PO_OK = 0,
+    PO_ERR_ARG = -1,         /* invalid argument (bad strand / metric / pattern / alignment) */
+    PO_ERR_CUDA = -2,        /* a CUDA runtime call or kernel launch failed */
+    PO_ERR_UNSUPPORTED = -3, /* valid request outside the implemented envelope */
+    PO_ERR_NODEVICE = -4     /* no CUDA device / not an sm_100 device */
+};
+
+/* select_strand(), bin/phyloligo.py:124-149 */
+enum po_strand { PO_STRAND_PLUS = 0, PO_STRAND_MINUS = 1, PO_STRAND_BOTH = 2 };
+
+/* -d/--distance choices, bin/phyloligo.py:1010; unpack_distances, bin/phyloligo.py:159-164 */
+enum po_metric { PO_EUCL = 0, PO_JSD = 1, PO_KT = 2, PO_BC = 3, PO_SC = 4 };
+
+enum po_dtype { PO_F32 = 0, PO_F64 = 1 };
+
+/* flags of po_distance_block */
+#define PO_FLAG_SKIP_LOWER 1u /* skip 64x64 tiles that lie wholly below the diagonal          */
+#define PO_FLAG_MIRROR     2u /* tiles wholly above the diagonal are also written transposed */
+
+#define PO_MAX_PATTERN 32 /* longest spaced pattern (window width) */
+#define PO_MAX_K       10 /* most '1's in a pattern (4^10 bins)     */
+#define PO_TILE        64 /* distance tile edge                      */
+
+const char* po_version(void);
+const char* po_last_error(void);
+
+/* Number of SMs and compute capability of the current device. */
+int po_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/*
+ * Pattern geometry.  `pattern` is the '0'/'1' string of -p/--pattern (or "1"*k for
+ * -k, bin/phyloligo.py:1040-1041).  Characters other than '1' are don't-care
+ * positions, exactly as target_index at bin/phyloligo.py:622 treats them.
+ * width = len(pattern), k = number of '1', dim = 4^k.
+ */
+int po_pattern_info(const char* pattern, int* width, int* k, int64_t* dim);
+
+/*
+ * FASTA record index on the host -- replaces the SeqIO.parse(genome, "fasta")
+ * iteration at bin/phyloligo.py:87,114,154,869,914,959 (Biopython semantics:
+ * a record starts at a line beginning with '>', text before the first '>' is
+ * ignored, the sequence is every later line up to the next header with
+ * whitespace removed).  Writes, for each record, the byte range [begin, end) of
+ * its sequence lines inside `h_text`.  Returns the number of records found (it
+ * may exceed `cap`, in which case only `cap` entries were written), or a
+ * negative po_status.  `threads` <= 0 picks a default.
+ */
+int64_t po_fasta_index_host(const uint8_t* h_text, int64_t len,
+                            int64_t* h_begin, int64_t* h_end, int64_t cap, int threads);
+
+/*
+ * Composition profiling of n records -- replaces compute_frequency
+ * (bin/phyloligo.py:663-691), compute_frequency_memmap (:693-720) and
+ * compute_frequency_h5py_chunk (:756-792), i.e. select_strand (:124-149) +
+ * .upper() (:683) + cut_sequence_and_count_pattern (:601-631) + count2freq
+ * (:633-661) for every record of a batch.
+ *
+ *   d_text            raw FASTA text (or bare sequence bytes); 16-byte aligned
+ *   d_begin, d_end    per record, byte range of its sequence inside d_text;
+ *                     bytes '\n', '\r' and ' ' inside a range are skipped
+ *   pattern, strand   as on the command line; strand is a po_strand
+ *   d_counts          [n x dim] uint32 word counts in C,G,A,T product order
+ *                     (bin/phyloligo.py:653), or NULL
+ *   d_totals          [n] uint64 number of counted words (kword_count), or NULL
+ *   d_freq64          [n x dim] float64 count/total, correctly rounded -- the
+ *                     --large None dtype (bin/phyloligo.py:656), or NULL
+ *   d_freq32          [n x dim] float32 cast of that float64 quotient -- the
+ *                     memmap / h5py dtype (bin/phyloligo.py:720,777-786), or NULL
+ * A record with no countable word gives an all-zero row (bin/phyloligo.py:660).
+ */
+int po_profile_batch(const uint8_t* d_text, const int64_t* d_begin, const int64_t* d_end,
+                     int64_t n, const char* pattern, int strand,
+                     uint32_t* d_counts, uint64_t* d_totals,
+                     double* d_freq64, float* d_freq32, po_stream_t stream);
+
+/*
+ * Size in bytes of one prepared row for `metric` at profile dimension `dim`
+ * (the operand layout po_distance_block consumes):
+ *   Eucl / JSD / BC : dim rounded up to a multiple of 4, float32
+ *   SC              : the same count of int32 (centred doubled average ranks)
+ *   KT              : packed order-relation bit masks, 2 * ceil(dim(dim-1)/2 / 128) * 16 bytes
+ */
+int64_t po_prepared_row_bytes(int metric, int64_t dim);
+
+/*
+ * Prepare the operand matrix for a metric from raw profiles.
+ *   d_X       [n x ldx] profiles, float32 or float64 (`dtype`), ldx in elements
+ *   d_P       [n x po_prepared_row_bytes] prepared rows (written)
+ *   d_aux     [n] float64 per-row constant (written):
+ *               SC: sum of squares of the centred doubled ranks (0 = constant row)
+ *               KT: number of element pairs that are not tied in the row
+ *               others: unused (may be NULL)
+ * Eucl/JSD/BC: a float32 copy, zero padded.  SC: rank transform with average
+ * ranks for ties -- the scipy.stats.spearmanr step of phylodist.SC
+ * (core/phylodist.py:82-85).  KT: the per-row half of Bio.Cluster's kendall()
+ * loop (core/phylodist.py:71-74): which element pairs are ordered up / down.
+ */
+int po_prepare_profiles(int metric, const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx,
+                        void* d_P, double* d_aux, po_stream_t stream);
+
+/*
+ * One block of the all-by-all distance matrix -- replaces the slice workers
+ * distances_loc / *_loc (bin/phyloligo.py:195-222), distances_h5py / *_h5py
+ * (:233-301), compute_unpack (:166-171) and the phylodist pair functions Eucl,
+ * JSD, KT, BC, SC (core/phylodist.py:36-85):
+ *
+ *   out[(r - out_row0) * ld_out + (c - out_col0)] = metric(profile r, profile c)
+ *   for r in [row0, row1), c in [col0, col1).
+ *
+ *   d_P, d_aux   prepared operands of all n rows (po_prepare_profiles)
+ *   out_dtype    PO_F32 (the --large dtypes) or PO_F64 (the --large None dtype)
+ *   flags        PO_FLAG_SKIP_LOWER / PO_FLAG_MIRROR exploit symmetry when the
+ *                caller's `out` addresses the full matrix (mirrored entries
+ *                (c, r) must be addressable).
+ * Values: Eucl = sqrt(sum (a-b)^2); JSD in nats (core/phylodist.py:22), 0 for
+ * identical rows, ln(2)/2 against an all-zero row; BC = sum|a-b| / sum|a+b|;
+ * KT = 1 - (1 - tau_b) (tau_b itself; 0 when a row is constant); SC = 1 - rho
+ * (NaN when a row is constant).
+ */
+int po_distance_block(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim,
+                      int64_t row0, int64_t row1, int64_t col0, int64_t col1,
+                      void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0,
+                      int out_dtype, unsigned flags, po_stream_t stream);
+
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+int64_t po_launch_count(void);
+
+/* Average device time (ms) of the launches of one kernel family since the last
+ * po_timing_reset(): CUDA events recorded on the launching stream around each
+ * launch while timing is enabled.  family: 0 = profiling, 1 = distance tile. */
+int po_timing_enable(int on);
+int po_timing_reset(void);
+int po_timing_read(int family, double* total_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYLOLIGO_B200_H */

@@ -1,0 +1,389 @@
+// All-by-all distance tiles on sm_100a CUDA cores: Eucl, JSD, BC, SC, KT.
+//
+// Replaces phylodist.Eucl/JSD/KT/BC/SC (reference core/phylodist.py:36-85) and the
+// block-row slice workers *_loc / *_h5py (bin/phyloligo.py:195-301).
+//
+// One CTA computes a 64 x 64 tile of the matrix.  256 threads; thread (ty, tx)
+// owns the 4 x 4 pairs (rows ty+16i, cols tx+16j).  Operand rows are "prepared
+// rows" of 32-bit elements (po_prepare_profiles): float32 profiles (Eucl, JSD,
+// BC), int32 centred doubled ranks (SC) or packed order-relation bit masks (KT).
+// The K dimension is streamed in chunks of 32 elements through a double-buffered
+// cp.async pipeline into shared memory with a row pitch of 36 words, which makes
+// the strided 128-bit operand reads bank-conflict free.  Partial sums are kept
+// in float32 for one chunk (32 non-negative terms) and folded into float64 (or
+// int64) accumulators per chunk, so the result carries no long-sum rounding.
+//
+// JSD.  The reference computes 0.5*sum(a ln(a/h) + b ln(b/h)), h = (a+b)/2, in
+// nats with 0*ln0 := 0.  Per dimension this kernel evaluates the identical
+// quantity in a cancellation-free form.  With s = a+b, d = a-b, x = d/s, u = x^2:
+//     a ln(a/h) + b ln(b/h) = (s/2) * f(x),   f(x) = (1+x)ln(1+x) + (1-x)ln(1-x) >= 0
+//     f(x) = u * G(u),  G(u) = sum_{n>=1} u^(n-1) / (n(2n-1))        (u <= 1/2)
+//     f(x) = E(w) + w ln w,  w = 1-|x| = 2 min(a,b)/s, E(w)=(2-w)ln(2-w)  (u > 1/2)
+// Every term is >= 0, so the sum has no cancellation; G and E are polynomial fits
+// at float32 rounding level (tools/jsd_poly_fit.py) and the only transcendental is
+// one MUFU.LG2 whose argument is < 0.15, where its error is relative (2 ulp).
+// No fast-math flags are used; the a = b = 0 case yields exactly 0.
+#include "po_common.cuh"
+
+namespace po {
+
+constexpr int TILE = PO_TILE;   // 64
+constexpr int DK = 32;          // K elements per pipeline stage
+constexpr int PITCH = DK + 4;   // smem row pitch in words
+constexpr int NTHREADS = 256;
+
+enum Kind { K_EUCL = 0, K_JSD = 1, K_KT = 2, K_BC = 3, K_SC = 4 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- per-dimension JSD term, returns s * f(x) = 4 * (contribution to JSD) ----
+__device__ __forceinline__ float jsd_term(float a, float b) {
+    const float s = fmaxf(a + b, 1e-30f);
+    const float d = a - b;
+    float rs = rcp_approx(s);
+    rs = fmaf(rs, fmaf(-s, rs, 1.0f), rs);  // one Newton step: correctly-rounded-level 1/s
+    const float x = d * rs;
+    const float u = x * x;
+    const float q = d * x;  // = s * u
+    // regime A: G(u) on [0, 1/2], degree 7
+    float G = 5.809747504e-02f;
+    G = fmaf(G, u, -4.418099709e-02f);
+    G = fmaf(G, u, 4.228754936e-02f);
+    G = fmaf(G, u, 1.528030711e-02f);
+    G = fmaf(G, u, 3.664686569e-02f);
+    G = fmaf(G, u, 6.660644403e-02f);
+    G = fmaf(G, u, 1.666681249e-01f);
+    G = fmaf(G, u, 9.999999943e-01f);
+    // regime B: f = E(w) + w ln w with v = w/2 = min(a,b)/s in [0, 0.1465]
+    const float v = fminf(a, b) * rs;
+    //   E(2v) + 2 ln2 * v  folded into one polynomial in v (degree 4)
+    float E = 2.100300184e-01f;                 // 16 * 1.312687615e-02
+    E = fmaf(E, v, 3.274813073e-01f);           //  8 * 4.093516341e-02
+    E = fmaf(E, v, 1.000313256e+00f);           //  4 * 2.500783139e-01
+    E = fmaf(E, v, -2.000005795e+00f);          //  2 * -1.693150078 + 2 ln 2
+    E = fmaf(E, v, 1.386294378e+00f);
+    const float vl = v * 1.386294361f;          // 2 ln2 * v
+    const float l2 = lg2_approx(fmaxf(v, 1e-37f));
+    const float fB = fmaf(vl, l2, E);           // = E(w) + w ln w
+    const bool regB = u > 0.5f;
+    return (regB ? s : q) * (regB ? fB : G);
+}
+
+template <int KIND>
+struct Accum {};
+
+template <>
+struct Accum<K_EUCL> {
+    float c[4][4];
+    double t[4][4];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { c[i][j] = 0.f; t[i][j] = 0.0; }
+    }
+    __device__ __forceinline__ void term(int i, int j, float a, float b) {
+        const float d = a - b;
+        c[i][j] = fmaf(d, d, c[i][j]);
+    }
+    __device__ __forceinline__ void fold() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { t[i][j] += (double)c[i][j]; c[i][j] = 0.f; }
+    }
+    __device__ __forceinline__ double result(int i, int j, double, double) const { return sqrt(t[i][j]); }
+};
+
+template <>
+struct Accum<K_JSD> {
+    float c[4][4];
+    double t[4][4];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { c[i][j] = 0.f; t[i][j] = 0.0; }
+    }
+    __device__ __forceinline__ void term(int i, int j, float a, float b) { c[i][j] += jsd_term(a, b); }
+    __device__ __forceinline__ void fold() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { t[i][j] += (double)c[i][j]; c[i][j] = 0.f; }
+    }
+    __device__ __forceinline__ double result(int i, int j, double, double) const { return 0.25 * t[i][j]; }
+};
+
+template <>
+struct Accum<K_BC> {  // sum|a-b|; the denominator sum|a+b| = sum a + sum b for non-negative profiles (aux)
+    float c[4][4];
+    double t[4][4];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { c[i][j] = 0.f; t[i][j] = 0.0; }
+    }
+    __device__ __forceinline__ void term(int i, int j, float a, float b) { c[i][j] += fabsf(a - b); }
+    __device__ __forceinline__ void fold() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { t[i][j] += (double)c[i][j]; c[i][j] = 0.f; }
+    }
+    __device__ __forceinline__ double result(int i, int j, double sa, double sb) const {
+        return t[i][j] / (sa + sb);  // 0/0 -> NaN, as scipy's braycurtis
+    }
+};
+
+template <>
+struct Accum<K_SC> {  // exact integer dot product of centred doubled ranks
+    int c[4][4];
+    long long t[4][4];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { c[i][j] = 0; t[i][j] = 0; }
+    }
+    __device__ __forceinline__ void term(int i, int j, float a, float b) {
+        c[i][j] += __float_as_int(a) * __float_as_int(b);
+    }
+    __device__ __forceinline__ void fold() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { t[i][j] += (long long)c[i][j]; c[i][j] = 0; }
+    }
+    __device__ __forceinline__ double result(int i, int j, double ssa, double ssb) const {
+        const double den = sqrt(ssa * ssb);
+        if (den == 0.0) return __longlong_as_double(0x7FF8000000000000ll);  // scipy: NaN for a constant row
+        return 1.0 - (double)t[i][j] / den;
+    }
+};
+
+template <>
+struct Accum<K_KT> {  // concordant - discordant element pairs from packed order masks
+    int c[4][4];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[i][j] = 0;
+    }
+    __device__ __forceinline__ void fold() {}
+    __device__ __forceinline__ double result(int i, int j, double ua, double ub) const {
+        // Bio.Cluster kendall(): distance 1 when a row is constant -> KT = 0;
+        // otherwise KT = 1 - (1 - tau), evaluated in that order for bit parity.
+        if (ua == 0.0 || ub == 0.0) return 0.0;
+        const double tau = (double)c[i][j] / sqrt(ua * ub);
+        return 1.0 - (1.0 - tau);
+    }
+};
+
+struct TileParams {
+    const uint32_t* P;    // prepared rows
+    const double* aux;    // per-row constants (SC, KT) or null
+    int64_t ldp;          // elements per prepared row (multiple of 4)
+    int64_t n;
+    int64_t row0, row1, col0, col1;
+    void* out;
+    int64_t ld_out, out_row0, out_col0;
+    unsigned flags;
+    int kdim;             // number of elements to stream (== ldp)
+};
+
+template <int KIND, typename OUT_T>
+__global__ void __launch_bounds__(NTHREADS, 2) distance_tile_kernel(const TileParams p) {
+    __shared__ __align__(16) uint32_t smem[2 * 2 * TILE * PITCH];  // [stage][A|B][row][PITCH]
+    const int64_t row_base = p.row0 + (int64_t)blockIdx.y * TILE;
+    const int64_t col_base = p.col0 + (int64_t)blockIdx.x * TILE;
+    if ((p.flags & PO_FLAG_SKIP_LOWER) && col_base + TILE <= row_base) return;
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+
+    // loader mapping: 64 rows x 8 float4 per operand = 512 float4, two per thread
+    const int lrow0 = tid >> 3, lc4 = tid & 7;  // rows lrow0 and lrow0 + 32
+    const int64_t nlast = p.n - 1;
+    const uint32_t* gA0 = p.P + min(row_base + lrow0, nlast) * p.ldp + lc4 * 4;
+    const uint32_t* gA1 = p.P + min(row_base + lrow0 + 32, nlast) * p.ldp + lc4 * 4;
+    const uint32_t* gB0 = p.P + min(col_base + lrow0, nlast) * p.ldp + lc4 * 4;
+    const uint32_t* gB1 = p.P + min(col_base + lrow0 + 32, nlast) * p.ldp + lc4 * 4;
+    const int nchunks = (p.kdim + DK - 1) / DK;
+
+    auto issue = [&](int chunk, int stage) {
+        uint32_t* sA = smem + stage * (2 * TILE * PITCH);
+        uint32_t* sB = sA + TILE * PITCH;
+        const int k0 = chunk * DK;
+        const bool ok = (k0 + lc4 * 4) < p.kdim;
+        cp_async16(sA + lrow0 * PITCH + lc4 * 4, gA0 + k0, ok);
+        cp_async16(sA + (lrow0 + 32) * PITCH + lc4 * 4, gA1 + k0, ok);
+        cp_async16(sB + lrow0 * PITCH + lc4 * 4, gB0 + k0, ok);
+        cp_async16(sB + (lrow0 + 32) * PITCH + lc4 * 4, gB1 + k0, ok);
+        cp_async_commit();
+    };
+
+    Accum<KIND> acc;
+    acc.init();
+
+    issue(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int stage = ch & 1;
+        if (ch + 1 < nchunks) {
+            issue(ch + 1, stage ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const uint32_t* sA = smem + stage * (2 * TILE * PITCH);
+        const uint32_t* sB = sA + TILE * PITCH;
+        if constexpr (KIND == K_KT) {
+            // elements come in groups of 8 words: 4 "up" masks then 4 "down" masks
+#pragma unroll
+            for (int g8 = 0; g8 < DK / 8; ++g8) {
+                uint4 ua[4], da[4], ub[4], db[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    ua[i] = *reinterpret_cast<const uint4*>(sA + (ty + 16 * i) * PITCH + g8 * 8);
+                    da[i] = *reinterpret_cast<const uint4*>(sA + (ty + 16 * i) * PITCH + g8 * 8 + 4);
+                    ub[i] = *reinterpret_cast<const uint4*>(sB + (tx + 16 * i) * PITCH + g8 * 8);
+                    db[i] = *reinterpret_cast<const uint4*>(sB + (tx + 16 * i) * PITCH + g8 * 8 + 4);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t au[4] = {ua[i].x, ua[i].y, ua[i].z, ua[i].w};
+                        const uint32_t ad[4] = {da[i].x, da[i].y, da[i].z, da[i].w};
+                        const uint32_t bu[4] = {ub[j].x, ub[j].y, ub[j].z, ub[j].w};
+                        const uint32_t bd[4] = {db[j].x, db[j].y, db[j].z, db[j].w};
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            const uint32_t con = (au[w] & bu[w]) | (ad[w] & bd[w]);
+                            const uint32_t dis = (au[w] & bd[w]) | (ad[w] & bu[w]);
+                            acc.c[i][j] += __popc(con) - __popc(dis);
+                        }
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int d4 = 0; d4 < DK / 4; ++d4) {
+                float4 a4[4], b4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    a4[i] = *reinterpret_cast<const float4*>(sA + (ty + 16 * i) * PITCH + d4 * 4);
+                    b4[i] = *reinterpret_cast<const float4*>(sB + (tx + 16 * i) * PITCH + d4 * 4);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc.term(i, j, a4[i].x, b4[j].x);
+                        acc.term(i, j, a4[i].y, b4[j].y);
+                        acc.term(i, j, a4[i].z, b4[j].z);
+                        acc.term(i, j, a4[i].w, b4[j].w);
+                    }
+            }
+            acc.fold();
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: stage the tile in shared memory, then coalesced stores (and the mirror) ----
+    OUT_T* tile = reinterpret_cast<OUT_T*>(smem);  // [TILE][TILE + 1]
+    constexpr int TP = TILE + 1;
+    static_assert(sizeof(OUT_T) * TILE * TP <= sizeof(uint32_t) * 2 * 2 * TILE * PITCH, "tile staging fits");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = row_base + ty + 16 * i;
+        const double auxr = (p.aux && r < p.n) ? p.aux[r] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t c = col_base + tx + 16 * j;
+            const double auxc = (p.aux && c < p.n) ? p.aux[c] : 0.0;
+            tile[(ty + 16 * i) * TP + tx + 16 * j] = (OUT_T)acc.result(i, j, auxr, auxc);
+        }
+    }
+    __syncthreads();
+    OUT_T* out = reinterpret_cast<OUT_T*>(p.out);
+    const int64_t rmax = min((int64_t)TILE, p.row1 - row_base);
+    const int64_t cmax = min((int64_t)TILE, p.col1 - col_base);
+    for (int e = tid; e < TILE * TILE; e += NTHREADS) {
+        const int r = e >> 6, c = e & 63;
+        if (r < rmax && c < cmax)
+            out[(row_base + r - p.out_row0) * p.ld_out + (col_base + c - p.out_col0)] = tile[r * TP + c];
+    }
+    if ((p.flags & PO_FLAG_MIRROR) && row_base + TILE <= col_base) {
+        for (int e = tid; e < TILE * TILE; e += NTHREADS) {
+            const int c = e >> 6, r = e & 63;  // consecutive threads walk r: contiguous in the mirrored row
+            if (r < rmax && c < cmax)
+                out[(col_base + c - p.out_row0) * p.ld_out + (row_base + r - p.out_col0)] = tile[r * TP + c];
+        }
+    }
+}
+
+template <int KIND>
+static int launch_kind(const TileParams& p, int out_dtype, dim3 grid, cudaStream_t stream) {
+    LaunchTimer t(1, stream);
+    if (out_dtype == PO_F32)
+        distance_tile_kernel<KIND, float><<<grid, NTHREADS, 0, stream>>>(p);
+    else
+        distance_tile_kernel<KIND, double><<<grid, NTHREADS, 0, stream>>>(p);
+    count_launch(1);
+    PO_LAUNCH_CHECK("distance_tile_kernel");
+    return PO_OK;
+}
+
+int launch_distance(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim,
+                    int64_t row0, int64_t row1, int64_t col0, int64_t col1,
+                    void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0,
+                    int out_dtype, unsigned flags, cudaStream_t stream) {
+    if (row1 <= row0 || col1 <= col0) return PO_OK;
+    TileParams p;
+    p.P = reinterpret_cast<const uint32_t*>(d_P);
+    p.aux = d_aux;
+    p.ldp = prepared_row_elems(metric, dim);
+    p.kdim = (int)p.ldp;
+    p.n = n;
+    p.row0 = row0; p.row1 = row1; p.col0 = col0; p.col1 = col1;
+    p.out = d_out; p.ld_out = ld_out; p.out_row0 = out_row0; p.out_col0 = out_col0;
+    p.flags = flags;
+    const int64_t tr = (row1 - row0 + TILE - 1) / TILE, tc = (col1 - col0 + TILE - 1) / TILE;
+    if (tr > 65535) {
+        set_error("row block too tall: %lld rows (max %d per call)", (long long)(row1 - row0), 65535 * TILE);
+        return PO_ERR_UNSUPPORTED;
+    }
+    dim3 grid((unsigned)tc, (unsigned)tr, 1);
+    switch (metric) {
+        case PO_EUCL: return launch_kind<K_EUCL>(p, out_dtype, grid, stream);
+        case PO_JSD: return launch_kind<K_JSD>(p, out_dtype, grid, stream);
+        case PO_BC: return launch_kind<K_BC>(p, out_dtype, grid, stream);
+        case PO_SC: return launch_kind<K_SC>(p, out_dtype, grid, stream);
+        case PO_KT: return launch_kind<K_KT>(p, out_dtype, grid, stream);
+    }
+    set_error("unknown metric %d", metric);
+    return PO_ERR_ARG;
+}
+
+}  // namespace po

@@ -1,0 +1,222 @@
+// Per-row operand preparation for the distance tiles (sm_100a).
+//
+//   Eucl / JSD : float32 copy of the profile, zero padded to a multiple of 4.
+//   BC         : the same copy; aux = sum of the row (the sum|a+b| denominator of
+//                scipy's braycurtis splits into row sums for non-negative profiles;
+//                a negative entry poisons aux with NaN so the result is loudly NaN).
+//   SC         : rank transform with average ranks for ties -- the
+//                scipy.stats.spearmanr step of phylodist.SC (core/phylodist.py:82-85).
+//                Stored as the integer 2*rank - (dim+1) = 2*less + equal - dim, which
+//                is exact, already centred (ranks always average (dim+1)/2) and makes
+//                the pairwise dot product an exact integer.  aux = sum of squares.
+//   KT         : the per-row half of Bio.Cluster's kendall() loop
+//                (core/phylodist.py:71-74).  Element pairs are enumerated as
+//                (i, (i+d) mod dim), d = 1 .. dim/2, bit e = (d-1)*dim + i; one mask
+//                holds "value_i > value_j", one "value_i < value_j".  Words are
+//                interleaved in groups of 4 up-words then 4 down-words so the tile
+//                kernel reads them with 128-bit loads.  aux = number of untied pairs.
+#include "po_common.cuh"
+
+namespace po {
+
+int64_t prepared_row_elems(int metric, int64_t dim) {
+    if (metric == PO_KT) {
+        const int64_t nbits = dim * (dim - 1) / 2;
+        const int64_t groups = (nbits + 127) / 128;  // 4 words of 32 bits per group
+        return (groups > 0 ? groups : 1) * 8;
+    }
+    return (dim + 3) / 4 * 4;
+}
+
+template <typename T>
+__device__ __forceinline__ double load_as_double(const void* X, int64_t idx) {
+    return (double)reinterpret_cast<const T*>(X)[idx];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) prepare_copy_kernel(const void* __restrict__ X, int64_t n, int64_t dim,
+                                                           int64_t ldx, float* __restrict__ P, int64_t ldp,
+                                                           double* __restrict__ aux, int want_sum) {
+    const int64_t row = blockIdx.x;
+    double s = 0.0;
+    bool neg = false;
+    for (int64_t e = threadIdx.x; e < ldp; e += blockDim.x) {
+        float v = 0.f;
+        if (e < dim) {
+            const double x = load_as_double<T>(X, row * ldx + e);
+            v = (float)x;
+            s += (double)v;
+            neg |= (v < 0.f);
+        }
+        P[row * ldp + e] = v;
+    }
+    if (want_sum) {
+        __shared__ double red[8];
+        __shared__ int sneg;
+        if (threadIdx.x == 0) sneg = 0;
+        __syncthreads();
+        if (neg) atomicOr(&sneg, 1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+            aux[row] = sneg ? __longlong_as_double(0x7FF8000000000000ll) : t;
+        }
+    }
+}
+
+// SC: centred doubled average ranks, O(dim^2) comparisons per row out of shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) prepare_rank_kernel(const void* __restrict__ X, int64_t n, int64_t dim,
+                                                           int64_t ldx, int* __restrict__ P, int64_t ldp,
+                                                           double* __restrict__ aux) {
+    extern __shared__ double srow[];
+    __shared__ unsigned long long s_ss;
+    const int64_t row = blockIdx.x;
+    for (int64_t e = threadIdx.x; e < dim; e += blockDim.x) srow[e] = load_as_double<T>(X, row * ldx + e);
+    if (threadIdx.x == 0) s_ss = 0ull;
+    __syncthreads();
+    unsigned long long ss = 0ull;
+    for (int64_t e = threadIdx.x; e < ldp; e += blockDim.x) {
+        int val = 0;
+        if (e < dim) {
+            const double v = srow[e];
+            int less = 0, eq = 0;
+            for (int64_t j = 0; j < dim; ++j) {
+                const double w = srow[j];
+                less += (w < v);
+                eq += (w == v);
+            }
+            val = 2 * less + eq - (int)dim;
+            ss += (unsigned long long)((long long)val * (long long)val);
+        }
+        P[row * ldp + e] = val;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+    if ((threadIdx.x & 31) == 0 && ss) atomicAdd(&s_ss, ss);
+    __syncthreads();
+    if (threadIdx.x == 0) aux[row] = (double)s_ss;
+}
+
+// KT: packed order-relation masks.
+template <typename T>
+__global__ void __launch_bounds__(256) prepare_kendall_kernel(const void* __restrict__ X, int64_t n, int64_t dim,
+                                                              int64_t ldx, uint32_t* __restrict__ P, int64_t ldp,
+                                                              double* __restrict__ aux) {
+    extern __shared__ double srow[];
+    __shared__ unsigned long long s_untied;
+    const int64_t row = blockIdx.x;
+    for (int64_t e = threadIdx.x; e < dim; e += blockDim.x) srow[e] = load_as_double<T>(X, row * ldx + e);
+    if (threadIdx.x == 0) s_untied = 0ull;
+    __syncthreads();
+    const int64_t nbits = dim * (dim - 1) / 2;
+    const int64_t nwords = ldp / 2;  // up-words (the same number of down-words)
+    unsigned long long untied = 0ull;
+    for (int64_t w = threadIdx.x; w < nwords; w += blockDim.x) {
+        uint32_t up = 0u, dn = 0u;
+        const int64_t e0 = w * 32;
+        if (e0 < nbits) {
+            int64_t d = e0 / dim + 1;
+            int64_t i = e0 % dim;
+#pragma unroll 4
+            for (int b = 0; b < 32; ++b) {
+                if (e0 + b < nbits) {
+                    int64_t j = i + d;
+                    if (j >= dim) j -= dim;
+                    const double vi = srow[i], vj = srow[j];
+                    up |= (uint32_t)(vi > vj) << b;
+                    dn |= (uint32_t)(vi < vj) << b;
+                }
+                if (++i == dim) { i = 0; ++d; }
+            }
+        }
+        untied += (unsigned)(__popc(up) + __popc(dn));
+        const int64_t g = w >> 2, q = w & 3;
+        P[row * ldp + g * 8 + q] = up;
+        P[row * ldp + g * 8 + 4 + q] = dn;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) untied += __shfl_xor_sync(0xFFFFFFFFu, untied, o);
+    if ((threadIdx.x & 31) == 0 && untied) atomicAdd(&s_untied, untied);
+    __syncthreads();
+    if (threadIdx.x == 0) aux[row] = (double)s_untied;
+}
+
+template <typename T>
+static int launch_prepare_t(int metric, const void* d_X, int64_t n, int64_t dim, int64_t ldx, void* d_P,
+                            double* d_aux, cudaStream_t stream) {
+    const int64_t ldp = prepared_row_elems(metric, dim);
+    const unsigned grid = (unsigned)n;
+    switch (metric) {
+        case PO_EUCL:
+        case PO_JSD:
+        case PO_BC: {
+            const int want_sum = (metric == PO_BC);
+            if (want_sum && !d_aux) {
+                set_error("BC needs d_aux");
+                return PO_ERR_ARG;
+            }
+            prepare_copy_kernel<T><<<grid, 256, 0, stream>>>(d_X, n, dim, ldx, (float*)d_P, ldp, d_aux, want_sum);
+            count_launch(2);
+            PO_LAUNCH_CHECK("prepare_copy_kernel");
+            return PO_OK;
+        }
+        case PO_SC: {
+            if (!d_aux) {
+                set_error("SC needs d_aux");
+                return PO_ERR_ARG;
+            }
+            const size_t sm = (size_t)dim * sizeof(double);
+            auto kern = prepare_rank_kernel<T>;
+            if (sm > 200 * 1024) {
+                set_error("SC: profile dimension %lld too large for the rank kernel", (long long)dim);
+                return PO_ERR_UNSUPPORTED;
+            }
+            if (sm > 48 * 1024)
+                PO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            kern<<<grid, 256, sm, stream>>>(d_X, n, dim, ldx, (int*)d_P, ldp, d_aux);
+            count_launch(2);
+            PO_LAUNCH_CHECK("prepare_rank_kernel");
+            return PO_OK;
+        }
+        case PO_KT: {
+            if (!d_aux) {
+                set_error("KT needs d_aux");
+                return PO_ERR_ARG;
+            }
+            const size_t sm = (size_t)dim * sizeof(double);
+            auto kern = prepare_kendall_kernel<T>;
+            if (sm > 200 * 1024) {
+                set_error("KT: profile dimension %lld too large for the mask kernel", (long long)dim);
+                return PO_ERR_UNSUPPORTED;
+            }
+            if (sm > 48 * 1024)
+                PO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            kern<<<grid, 256, sm, stream>>>(d_X, n, dim, ldx, (uint32_t*)d_P, ldp, d_aux);
+            count_launch(2);
+            PO_LAUNCH_CHECK("prepare_kendall_kernel");
+            return PO_OK;
+        }
+    }
+    set_error("unknown metric %d", metric);
+    return PO_ERR_ARG;
+}
+
+int launch_prepare(int metric, const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx,
+                   void* d_P, double* d_aux, cudaStream_t stream) {
+    if (n == 0) return PO_OK;
+    if (n > 0x7FFFFFFFll) {
+        set_error("too many rows (%lld)", (long long)n);
+        return PO_ERR_UNSUPPORTED;
+    }
+    if (dtype == PO_F32) return launch_prepare_t<float>(metric, d_X, n, dim, ldx, d_P, d_aux, stream);
+    if (dtype == PO_F64) return launch_prepare_t<double>(metric, d_X, n, dim, ldx, d_P, d_aux, stream);
+    set_error("unknown dtype %d", dtype);
+    return PO_ERR_ARG;
+}
+
+}  // namespace po

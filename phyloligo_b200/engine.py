@@ -1,0 +1,294 @@
+"""Host-side driver of the CUDA hot path: device buffers (torch), launches (C ABI).
+
+torch is used for allocation, streams and host<->device copies only; every
+computation happens in libphyloligo_b200.so.  Nothing here falls back to the
+CPU: without a CUDA device the functions raise PhyloligoError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PhyloligoError, METRICS, STRANDS, PO_F32, PO_F64, FLAG_MIRROR, FLAG_SKIP_LOWER, TILE
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise PhyloligoError("no CUDA device visible: phyloligo_b200 runs on B200 (sm_100a) only and has no CPU fallback")
+    _lib.load()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+# ----------------------------------------------------------------------------
+# FASTA
+# ----------------------------------------------------------------------------
+def as_u8(text) -> np.ndarray:
+    if isinstance(text, np.ndarray):
+        if text.dtype != np.uint8:
+            raise TypeError("text array must be uint8")
+        return np.ascontiguousarray(text)
+    if isinstance(text, torch.Tensor):
+        return text.numpy()
+    if isinstance(text, str):
+        text = text.encode("latin-1")
+    return np.frombuffer(text, dtype=np.uint8)
+
+
+def fasta_index(text, threads=0):
+    """Record index of FASTA text held in host memory: (begin, end) int64 arrays
+    of the byte range of every record's sequence lines (Biopython record rules,
+    reference call sites bin/phyloligo.py:87,114,154,869,914,959)."""
+    lib = _lib.load()
+    buf = as_u8(text)
+    n_bytes = buf.shape[0]
+    cap = max(1024, n_bytes // 2000)
+    while True:
+        begin = np.empty(cap, dtype=np.int64)
+        end = np.empty(cap, dtype=np.int64)
+        n = lib.po_fasta_index_host(buf.ctypes.data, n_bytes, begin.ctypes.data, end.ctypes.data, cap, threads)
+        _lib.check(n, "po_fasta_index_host")
+        if n <= cap:
+            return begin[:n].copy(), end[:n].copy()
+        cap = int(n)
+
+
+def sequences_to_text(seqs):
+    """Pack bare sequences (str/bytes) into one buffer, newline separated, with
+    their (begin, end) ranges -- the batch form of the per-sequence worker API."""
+    parts, begin, end = [], [], []
+    pos = 0
+    for s in seqs:
+        b = s.encode("latin-1") if isinstance(s, str) else bytes(s)
+        begin.append(pos)
+        end.append(pos + len(b))
+        parts.append(b)
+        parts.append(b"\n")
+        pos += len(b) + 1
+    text = np.frombuffer(b"".join(parts), dtype=np.uint8) if parts else np.zeros(0, dtype=np.uint8)
+    return text, np.asarray(begin, dtype=np.int64), np.asarray(end, dtype=np.int64)
+
+
+# ----------------------------------------------------------------------------
+# Profiling
+# ----------------------------------------------------------------------------
+def text_to_device(text, device=None, non_blocking=False):
+    """Copy FASTA bytes to the device, padded so 16-byte loads never leave the buffer."""
+    device = device or require_cuda()
+    if isinstance(text, torch.Tensor):
+        src = text
+    else:
+        src = torch.from_numpy(as_u8(text))
+    n = src.shape[0]
+    dst = torch.empty(n + 64, dtype=torch.uint8, device=device)
+    dst[:n].copy_(src, non_blocking=non_blocking)
+    dst[n:].fill_(10)
+    return dst
+
+
+def profile_device(d_text, d_begin, d_end, pattern, strand, want=("counts", "totals", "freq64")):
+    """Launch po_profile_batch on device tensors; returns a dict of device tensors."""
+    device = require_cuda()
+    lib = _lib.load()
+    pattern = str(pattern)
+    if strand not in STRANDS:
+        raise PhyloligoError("Error, strand parameter should be chosen from {'both', 'minus', 'plus'}")
+    _, _, dim = _lib.pattern_info(pattern)
+    n = int(d_begin.shape[0])
+    out = {}
+    counts = totals = f64 = f32 = None
+    if "counts" in want or dim * 4 > 160 * 1024:
+        counts = torch.empty((n, dim), dtype=torch.int32, device=device)
+    if "totals" in want:
+        totals = torch.empty((n,), dtype=torch.int64, device=device)
+    if "freq64" in want:
+        f64 = torch.empty((n, dim), dtype=torch.float64, device=device)
+    if "freq32" in want:
+        f32 = torch.empty((n, dim), dtype=torch.float32, device=device)
+    rc = lib.po_profile_batch(_ptr(d_text), _ptr(d_begin), _ptr(d_end), n, pattern.encode(), STRANDS[strand],
+                              _ptr(counts), _ptr(totals), _ptr(f64), _ptr(f32), _stream())
+    _lib.check(rc, "po_profile_batch")
+    if counts is not None and "counts" in want:
+        out["counts"] = counts
+    if totals is not None:
+        out["totals"] = totals
+    if f64 is not None:
+        out["freq64"] = f64
+    if f32 is not None:
+        out["freq32"] = f32
+    return out
+
+
+def profile_text(text, pattern, strand="both", want=("freq64",), begin=None, end=None):
+    """Profile every record of FASTA text in host memory; returns device tensors."""
+    device = require_cuda()
+    if begin is None:
+        begin, end = fasta_index(text)
+    d_text = text_to_device(text, device)
+    d_begin = torch.from_numpy(np.ascontiguousarray(begin)).to(device)
+    d_end = torch.from_numpy(np.ascontiguousarray(end)).to(device)
+    return profile_device(d_text, d_begin, d_end, pattern, strand, want)
+
+
+def profile_sequences(seqs, pattern, strand="both", want=("freq64",)):
+    text, begin, end = sequences_to_text(seqs)
+    return profile_text(text, pattern, strand, want, begin, end)
+
+
+# ----------------------------------------------------------------------------
+# Distances
+# ----------------------------------------------------------------------------
+def prepare(X, metric):
+    """po_prepare_profiles: X is a device tensor (n, dim) float32/float64.
+    Returns (P int32 tensor (n, row_elems), aux float64 tensor (n,), dim)."""
+    device = require_cuda()
+    lib = _lib.load()
+    if metric not in METRICS:
+        raise PhyloligoError("Error, unknown method {}".format(metric))
+    if X.dim() != 2:
+        raise PhyloligoError("profiles must be a 2-D matrix")
+    if X.dtype not in (torch.float32, torch.float64):
+        X = X.to(torch.float64)
+    X = X.contiguous()
+    n, dim = int(X.shape[0]), int(X.shape[1])
+    row_bytes = lib.po_prepared_row_bytes(METRICS[metric], dim)
+    _lib.check(row_bytes, "po_prepared_row_bytes")
+    P = torch.empty((n, row_bytes // 4), dtype=torch.int32, device=device)
+    aux = torch.zeros((n,), dtype=torch.float64, device=device)
+    rc = lib.po_prepare_profiles(METRICS[metric], _ptr(X), PO_F32 if X.dtype == torch.float32 else PO_F64,
+                                 n, dim, dim, _ptr(P), _ptr(aux), _stream())
+    _lib.check(rc, "po_prepare_profiles")
+    return P, aux, dim
+
+
+def distance_block(metric, P, aux, dim, row0, row1, col0, col1, out, out_row0, out_col0, flags=0):
+    """po_distance_block into the device tensor `out` (2-D, float32 or float64)."""
+    lib = _lib.load()
+    n = int(P.shape[0])
+    rc = lib.po_distance_block(METRICS[metric], _ptr(P), _ptr(aux), n, dim, row0, row1, col0, col1,
+                               _ptr(out), int(out.stride(0)), out_row0, out_col0,
+                               PO_F32 if out.dtype == torch.float32 else PO_F64, flags, _stream())
+    _lib.check(rc, "po_distance_block")
+
+
+def distance_matrix_device(X, metric, out_dtype=torch.float64, symmetric=True):
+    """Full n x n matrix resident on the device."""
+    device = require_cuda()
+    P, aux, dim = prepare(X, metric)
+    n = int(P.shape[0])
+    out = torch.empty((n, n), dtype=out_dtype, device=device)
+    flags = (FLAG_SKIP_LOWER | FLAG_MIRROR) if symmetric else 0
+    # row panels keep every grid dimension inside the launch limits
+    step = 65535 * TILE
+    for r0 in range(0, n, step):
+        distance_block(metric, P, aux, dim, r0, min(n, r0 + step), 0, n, out, 0, 0, flags)
+    if dim < 2 and metric == "KT":
+        out.fill_(1.0)  # kendall() with no element pair: distance 0 -> KT = 1
+    return out
+
+
+def pair_distance(a, b, metric):
+    """One pair through the tile kernel (the phylodist.<metric>(a, b) worker)."""
+    device = require_cuda()
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    if a.shape != b.shape:
+        raise PhyloligoError("profiles must have the same length")
+    X = torch.from_numpy(np.stack([a, b])).to(device)
+    out = distance_matrix_device(X, metric, torch.float64, symmetric=False)
+    return float(out[0, 1].item())
+
+
+class PanelStreamer:
+    """Compute the matrix in row panels and stream each finished panel to the host.
+
+    Symmetric mode keeps the whole n x n float32 matrix on the device (needs
+    4 n^2 bytes of HBM): panel p computes only the tiles right of the diagonal and
+    mirrors them, so by the time panel p is done its rows are complete and can
+    leave over PCIe while panel p+1 computes.  Otherwise each panel computes its
+    full rows into one of two panel buffers.
+    """
+
+    def __init__(self, X, metric, out_dtype=torch.float32, panel_rows=4096, symmetric=None, rows=None):
+        self.device = require_cuda()
+        self.metric = metric
+        self.P, self.aux, self.dim = prepare(X, metric)
+        self.n = int(self.P.shape[0])
+        self.out_dtype = out_dtype
+        self.panel_rows = max(TILE, (int(panel_rows) // TILE) * TILE)
+        esize = 4 if out_dtype == torch.float32 else 8
+        if symmetric is None:
+            free, _ = torch.cuda.mem_get_info()
+            symmetric = rows is None and self.n * self.n * esize < 0.6 * free
+        self.symmetric = bool(symmetric)
+        self.rows = rows  # optional (start, stop) row range owned by this rank
+        self.compute_stream = torch.cuda.current_stream()
+        self.copy_stream = torch.cuda.Stream()
+        if self.symmetric:
+            self.full = torch.empty((self.n, self.n), dtype=out_dtype, device=self.device)
+            self.bufs = None
+        else:
+            self.full = None
+            self.bufs = [torch.empty((self.panel_rows, self.n), dtype=out_dtype, device=self.device) for _ in range(2)]
+        self.pinned = [torch.empty((self.panel_rows, self.n), dtype=out_dtype).pin_memory() for _ in range(2)]
+        self.pairs_computed = 0
+
+    def panels(self):
+        lo, hi = (0, self.n) if self.rows is None else self.rows
+        r = lo
+        while r < hi:
+            yield r, min(hi, r + self.panel_rows)
+            r += self.panel_rows
+
+    def run(self, sink):
+        """sink(row0, row1, host_array) is called for every finished panel, in order.
+        host_array is a view of a pinned buffer valid only during the call."""
+        done_events = [None, None]   # copy finished -> pinned buffer may be consumed
+        free_events = [None, None]   # device panel buffer free again
+        pending = []                 # (slot, r0, r1)
+        k = 0
+        for r0, r1 in self.panels():
+            slot = k & 1
+            m = r1 - r0
+            if self.symmetric:
+                distance_block(self.metric, self.P, self.aux, self.dim, r0, r1, 0, self.n, self.full, 0, 0,
+                               FLAG_SKIP_LOWER | FLAG_MIRROR)
+                src = self.full[r0:r1]
+                for t0 in range(r0, r1, TILE):  # tiles left of the diagonal tile are skipped
+                    self.pairs_computed += (min(r1, t0 + TILE) - t0) * (self.n - t0)
+            else:
+                if free_events[slot] is not None:
+                    self.compute_stream.wait_event(free_events[slot])
+                distance_block(self.metric, self.P, self.aux, self.dim, r0, r1, 0, self.n, self.bufs[slot], r0, 0, 0)
+                src = self.bufs[slot][:m]
+                self.pairs_computed += m * self.n
+            ready = torch.cuda.Event()
+            ready.record(self.compute_stream)
+            # the pinned slot must have been consumed by the sink before it is overwritten
+            while pending and pending[0][0] == slot:
+                s, p0, p1 = pending.pop(0)
+                done_events[s].synchronize()
+                sink(p0, p1, self.pinned[s][: p1 - p0].numpy())
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(ready)
+                self.pinned[slot][:m].copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                done_events[slot] = ev
+                free_events[slot] = ev
+            pending.append((slot, r0, r1))
+            k += 1
+        for s, p0, p1 in pending:
+            done_events[s].synchronize()
+            sink(p0, p1, self.pinned[s][: p1 - p0].numpy())
+        return self.pairs_computed

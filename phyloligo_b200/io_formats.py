@@ -1,0 +1,255 @@
+"""On-disk formats of the reference, written without h5py (absent from this image).
+
+* text: ``np.savetxt(path, M, delimiter="\\t")`` -> ``%.18e`` fields, '\\n' rows
+  (reference bin/phyloligo.py:1059-1066).
+* memmap: raw row-major float32 N x N, no header (reference :413-417; readers
+  bin/phyloligo_comparemat.py:16-24, bin/phyloselect.py:606-614).
+* HDF5: one contiguous 2-D dataset named ``frequencies`` or ``distances``
+  (reference :471-478, :923-930, :787-792).  The writer below emits the classic
+  HDF5 layout (superblock v0, symbol-table root group, v1 object headers,
+  contiguous storage) so h5py / libhdf5 consumers can open it; the reader parses
+  that same subset.  It has been checked against its own reader only -- libhdf5
+  is not available in the build image.
+"""
+from __future__ import annotations
+
+import os
+import struct
+
+import numpy as np
+
+UNDEF = 0xFFFFFFFFFFFFFFFF
+_SIG = b"\x89HDF\r\n\x1a\n"
+
+
+def savetxt(path, arr):
+    np.savetxt(path, arr, delimiter="\t")
+
+
+def read_numpy(path):
+    return np.loadtxt(path)
+
+
+def read_memmap(path):
+    """Square float32 matrix from a raw file (shape from the file size)."""
+    m = np.memmap(path, dtype=np.float32, mode="r")
+    n = int(round(np.sqrt(m.shape[0])))
+    if n * n != m.shape[0]:
+        raise ValueError("Error, weird shape for matrix {}".format(path))
+    return m.reshape((n, n))
+
+
+# ---------------------------------------------------------------------------
+# minimal HDF5
+# ---------------------------------------------------------------------------
+def _pad8(b):
+    return b + b"\0" * ((-len(b)) % 8)
+
+
+def _msg(mtype, data, flags=0):
+    data = _pad8(data)
+    return struct.pack("<HHB3x", mtype, len(data), flags) + data
+
+
+def _dtype_message(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        size, sign, eloc, esize, mloc, msize, bias = 4, 31, 23, 8, 0, 23, 127
+    elif dtype == np.float64:
+        size, sign, eloc, esize, mloc, msize, bias = 8, 63, 52, 11, 0, 52, 1023
+    else:
+        raise TypeError("only float32/float64 datasets are supported")
+    head = struct.pack("<BBBBI", 0x11, 0x20, sign, 0, size)
+    props = struct.pack("<HHBBBBI", 0, size * 8, eloc, esize, mloc, msize, bias)
+    return head + props
+
+
+def _object_header(messages):
+    body = b"".join(messages)
+    return struct.pack("<BBHII4x", 1, 0, len(messages), 1, len(body)) + body
+
+
+def _layout(name, shape, dtype, align=4096):
+    """Return (header_bytes, data_offset, data_nbytes) of a one-dataset file."""
+    name_b = name.encode("ascii")
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    # fixed addresses
+    a_super = 0
+    a_root_oh = 96
+    root_oh_size = 16 + 8 + 16
+    a_btree = a_root_oh + root_oh_size          # 136
+    btree_size = 24 + (2 * 16 + 1) * 8 + 2 * 16 * 8
+    a_heap = a_btree + btree_size               # 680
+    heap_hdr = 32
+    name_off = 8
+    name_len = len(_pad8(name_b + b"\0"))
+    free_off = name_off + name_len
+    heap_data_size = free_off + 32
+    a_heap_data = a_heap + heap_hdr
+    a_snod = a_heap_data + heap_data_size
+    a_snod += (-a_snod) % 8
+    snod_size = 8 + 8 * 40
+    a_dset_oh = a_snod + snod_size
+    # dataset object header
+    dataspace = struct.pack("<BBB5x", 1, len(shape), 0) + b"".join(struct.pack("<Q", int(d)) for d in shape)
+    fill = struct.pack("<BBBB", 2, 1, 0, 0)
+    data_off_placeholder = 0
+    msgs_wo_layout = [_msg(0x0001, dataspace), _msg(0x0003, _dtype_message(dtype), flags=1), _msg(0x0005, fill)]
+    layout_len = len(_msg(0x0008, struct.pack("<BBQQ", 3, 1, 0, 0)))
+    oh_size = 16 + sum(len(m) for m in msgs_wo_layout) + layout_len
+    data_off = a_dset_oh + oh_size
+    data_off += (-data_off) % align
+    eof = data_off + nbytes
+    layout = _msg(0x0008, struct.pack("<BBQQ", 3, 1, data_off, nbytes))
+    dset_oh = _object_header(msgs_wo_layout + [layout])
+    assert len(dset_oh) == oh_size
+    del data_off_placeholder
+
+    sb = _SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, 4, 16, 0)
+    sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+    sb += struct.pack("<QQII", 0, a_root_oh, 1, 0) + struct.pack("<QQ", a_btree, a_heap)
+    assert len(sb) == 96
+    root_oh = _object_header([_msg(0x0011, struct.pack("<QQ", a_btree, a_heap))])
+    assert len(root_oh) == root_oh_size
+    btree = b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, UNDEF, UNDEF)
+    btree += struct.pack("<QQQ", 0, a_snod, name_off)
+    btree += b"\0" * (btree_size - len(btree))
+    heap = b"HEAP" + struct.pack("<B3xQQQ", 0, heap_data_size, free_off, a_heap_data)
+    heap_data = b"\0" * 8 + _pad8(name_b + b"\0") + struct.pack("<QQ", 1, heap_data_size - free_off)
+    heap_data += b"\0" * (heap_data_size - len(heap_data))
+    snod = b"SNOD" + struct.pack("<BBH", 1, 0, 1)
+    snod += struct.pack("<QQII16x", name_off, a_dset_oh, 0, 0)
+    snod += b"\0" * (snod_size - len(snod))
+
+    out = bytearray(data_off)
+    for addr, blob in ((a_super, sb), (a_root_oh, root_oh), (a_btree, btree), (a_heap, heap),
+                       (a_heap_data, heap_data), (a_snod, snod), (a_dset_oh, dset_oh)):
+        out[addr:addr + len(blob)] = blob
+    return bytes(out), data_off, nbytes
+
+
+class Hdf5DatasetWriter:
+    """Create an HDF5 file with one contiguous dataset and fill it row block by row block."""
+
+    def __init__(self, path, name, shape, dtype=np.float32):
+        self.path, self.shape, self.dtype = path, tuple(int(s) for s in shape), np.dtype(dtype)
+        header, self.data_off, self.nbytes = _layout(name, self.shape, self.dtype)
+        with open(path, "wb") as fh:
+            fh.write(header)
+            if self.nbytes:
+                fh.truncate(self.data_off + self.nbytes)
+        self.mm = None
+        if self.nbytes:
+            self.mm = np.memmap(path, dtype=self.dtype, mode="r+", offset=self.data_off, shape=self.shape)
+
+    def write_rows(self, row0, block):
+        self.mm[row0:row0 + block.shape[0]] = block
+
+    def close(self):
+        if self.mm is not None:
+            self.mm.flush()
+            del self.mm
+            self.mm = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
+def write_hdf5(path, name, array):
+    array = np.ascontiguousarray(array)
+    with Hdf5DatasetWriter(path, name, array.shape, array.dtype) as w:
+        if array.size:
+            w.mm[...] = array
+
+
+def _read_object_header(buf, addr):
+    version, _, nmsg, _, hsize = struct.unpack_from("<BBHII", buf, addr)
+    if version != 1:
+        raise ValueError("unsupported object header version %d" % version)
+    msgs = []
+    blocks = [(addr + 16, hsize)]
+    while blocks and len(msgs) < nmsg:
+        pos, size = blocks.pop(0)
+        end = pos + size
+        while pos + 8 <= end and len(msgs) < nmsg:
+            mtype, msize, _ = struct.unpack_from("<HHB", buf, pos)
+            data = bytes(buf[pos + 8:pos + 8 + msize])
+            pos += 8 + msize
+            if mtype == 0x0010:  # continuation
+                caddr, clen = struct.unpack_from("<QQ", data, 0)
+                blocks.append((caddr, clen))
+            msgs.append((mtype, data))
+    return msgs
+
+
+def _find_dataset(buf, name):
+    if bytes(buf[:8]) != _SIG:
+        raise ValueError("not an HDF5 file")
+    if buf[8] != 0 or buf[13] != 8 or buf[14] != 8:
+        raise ValueError("unsupported HDF5 superblock")
+    btree, heap = struct.unpack_from("<QQ", buf, 56 + 24)
+    if bytes(buf[heap:heap + 4]) != b"HEAP":
+        raise ValueError("bad local heap")
+    heap_data = struct.unpack_from("<Q", buf, heap + 24)[0]
+
+    def walk(node):
+        if bytes(buf[node:node + 4]) != b"TREE":
+            raise ValueError("bad B-tree node")
+        _, level, used = struct.unpack_from("<BBH", buf, node + 4)
+        pos = node + 24
+        for i in range(used):
+            child = struct.unpack_from("<Q", buf, pos + 8)[0]
+            pos += 16
+            if level > 0:
+                yield from walk(child)
+            else:
+                if bytes(buf[child:child + 4]) != b"SNOD":
+                    raise ValueError("bad symbol node")
+                nsym = struct.unpack_from("<H", buf, child + 6)[0]
+                for s in range(nsym):
+                    noff, oh = struct.unpack_from("<QQ", buf, child + 8 + 40 * s)
+                    p = heap_data + noff
+                    q = p
+                    while buf[q] != 0:
+                        q += 1
+                    yield bytes(buf[p:q]).decode("ascii"), oh
+
+    for nm, oh in walk(btree):
+        if nm == name:
+            return oh
+    raise KeyError(name)
+
+
+def read_hdf5(path, name):
+    """Read a contiguous float32/float64 dataset written by write_hdf5 (or any file
+    using the same classic layout)."""
+    buf = np.memmap(path, dtype=np.uint8, mode="r")
+    oh = _find_dataset(buf, name)
+    shape = dtype = None
+    addr = size = None
+    for mtype, data in _read_object_header(buf, oh):
+        if mtype == 0x0001:
+            ver, rank = data[0], data[1]
+            off = 8 if ver == 1 else 4
+            shape = tuple(struct.unpack_from("<Q", data, off + 8 * i)[0] for i in range(rank))
+        elif mtype == 0x0003:
+            cls = data[0] & 0x0F
+            sz = struct.unpack_from("<I", data, 4)[0]
+            if cls != 1 or sz not in (4, 8):
+                raise ValueError("unsupported datatype")
+            dtype = np.float32 if sz == 4 else np.float64
+        elif mtype == 0x0008:
+            if data[0] != 3 or data[1] != 1:
+                raise ValueError("unsupported data layout")
+            addr, size = struct.unpack_from("<QQ", data, 2)
+    if shape is None or dtype is None or addr is None:
+        raise ValueError("incomplete dataset header")
+    n = int(np.prod(shape, dtype=np.int64))
+    if n == 0:
+        return np.zeros(shape, dtype=dtype)
+    return np.array(np.memmap(path, dtype=dtype, mode="r", offset=addr, shape=shape))

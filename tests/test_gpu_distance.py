@@ -1,0 +1,163 @@
+"""GPU parity: po_prepare_profiles + po_distance_block (through the C ABI) against
+the reference golden matrices and the oracle.
+
+Tolerances (BASELINE.json north_star): Eucl / BC / JSD <= 1e-6 relative against the
+float64-accumulated oracle on the same inputs; KT and SC exact up to float64
+rounding of the final division (1e-12)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import phylo_oracle as po
+from phyloligo_b200 import engine, phylodist, synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6
+
+
+def _gpu_matrix(X, metric, out_dtype=torch.float64, symmetric=True):
+    Xd = torch.from_numpy(np.ascontiguousarray(X)).cuda()
+    return engine.distance_matrix_device(Xd, metric, out_dtype, symmetric).cpu().numpy()
+
+
+def _profiles(n, mean_len, pattern, seed, dtype=np.float64):
+    seqs = synth.make_sequences(n, mean_len, seed=seed)
+    return np.vstack([po.frequency_np(s, pattern, "both", dtype) for s in seqs])
+
+
+def _assert_close(got, want, rtol=RTOL, atol=0.0):
+    err = np.abs(got - want)
+    tol = rtol * np.abs(want) + atol
+    bad = err > tol
+    assert not bad.any(), "max rel err %.3e at %s" % (
+        (err / np.maximum(np.abs(want), 1e-300)).max(), np.argwhere(bad)[:5].tolist())
+
+
+def test_golden_matrices(distance_golden):
+    for name in ("real_k4", "sparse_64", "onehot_16"):
+        X = distance_golden[name + "_X"]
+        # oracle on the float32-rounded inputs the kernel consumes, float64 accumulation
+        X32 = X.astype(np.float32).astype(np.float64)
+        for metric in ("Eucl", "JSD"):
+            got = _gpu_matrix(X, metric)
+            _assert_close(got, po.pairwise_np(X32, metric), atol=1e-12)
+            # and against the reference's own float64 output on the float64 inputs
+            ref = distance_golden[name + "_" + metric]
+            assert np.allclose(got, ref, rtol=5e-6, atol=1e-9)
+            assert np.array_equal(got, got.T)
+            assert (np.diag(got) == 0).all()
+    e = np.eye(16)[:6]
+    got = _gpu_matrix(e, "JSD")
+    off = got[~np.eye(6, dtype=bool)]
+    assert np.allclose(off, np.log(2), rtol=1e-6)
+
+
+@pytest.mark.parametrize("metric", ["Eucl", "JSD", "BC"])
+@pytest.mark.parametrize("pattern,n,length", [("1111", 150, 4000), ("11111", 70, 2000), ("111010011", 66, 3000)])
+def test_float_metrics_vs_fp64_oracle(metric, pattern, n, length):
+    X = _profiles(n, length, pattern, seed=31, dtype=np.float32)
+    X[3] = 0.0  # an empty contig: all-zero profile
+    want = po.pairwise_np(X.astype(np.float64), metric)
+    for out_dtype, rt in ((torch.float64, RTOL), (torch.float32, RTOL)):
+        got = _gpu_matrix(X, metric, out_dtype).astype(np.float64)
+        mask = np.isfinite(want)
+        assert np.array_equal(np.isnan(got), np.isnan(want))  # BC of two zero rows: 0/0
+        _assert_close(got[mask], want[mask], rtol=rt, atol=1e-12)
+    full = _gpu_matrix(X, metric, torch.float64, symmetric=False)
+    sym = _gpu_matrix(X, metric, torch.float64, symmetric=True)
+    assert np.array_equal(full, sym, equal_nan=True)  # mirrored tiles are bitwise the computed ones
+
+
+def test_jsd_edge_values():
+    z = np.zeros(256)
+    a = np.full(256, 1.0 / 256)
+    X = np.vstack([z, a, a, np.eye(256)[0], np.eye(256)[1]])
+    got = _gpu_matrix(X, "JSD")
+    assert got[0, 0] == 0.0 and got[1, 2] == 0.0
+    assert got[0, 1] == pytest.approx(0.5 * np.log(2), rel=1e-6)   # against an all-zero row
+    assert got[3, 4] == pytest.approx(np.log(2), rel=1e-6)
+    assert (got >= 0).all() and (got <= np.log(2) * (1 + 1e-6)).all()
+
+
+def test_jsd_near_identical_profiles_keep_relative_accuracy():
+    rng = np.random.default_rng(3)
+    base = rng.random(1024)
+    base /= base.sum()
+    rows = [base]
+    for eps in (1e-1, 1e-2, 1e-3):
+        r = base * (1 + eps * rng.standard_normal(1024))
+        rows.append(np.abs(r) / np.abs(r).sum())
+    X = np.vstack(rows).astype(np.float32)
+    got = _gpu_matrix(X, "JSD")
+    want = po.pairwise_np(X.astype(np.float64), "JSD")
+    off = ~np.eye(len(rows), dtype=bool)
+    assert (np.abs(got[off] / want[off] - 1) < 2e-6).all()
+
+
+@pytest.mark.parametrize("metric", ["KT", "SC"])
+def test_rank_metrics_exact(metric):
+    # tie-heavy short-read profiles (config C4 shape) plus constant / empty rows
+    seqs = synth.make_sequences(60, 375, seed=4, model="short")
+    X = np.vstack([po.frequency_np(s, "1111", "both") for s in seqs])
+    X[7] = 0.0
+    X[9] = 1.0 / 256
+    got = _gpu_matrix(X, metric)
+    fn = po.KT if metric == "KT" else po.SC
+    n = X.shape[0]
+    want = np.array([[fn(X[i], X[j]) for j in range(n)] for i in range(n)])
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    m = ~np.isnan(want)
+    assert np.abs(got[m] - want[m]).max() < 1e-12
+    if metric == "KT":
+        assert (got[7] == 0).all() and (got[9] == 0).all()
+        assert np.array_equal(got, want)  # integer counts, same float64 expression: bit exact
+
+
+def test_rank_metrics_small_dims():
+    rng = np.random.default_rng(2)
+    for dim in (2, 3, 5, 16, 33, 64):
+        X = rng.integers(0, 3, size=(9, dim)).astype(np.float64)
+        for metric, fn in (("KT", po.KT), ("SC", po.SC)):
+            got = _gpu_matrix(X, metric)
+            want = np.array([[fn(a, b) for b in X] for a in X])
+            assert np.array_equal(np.isnan(got), np.isnan(want)), (metric, dim)
+            m = ~np.isnan(want)
+            assert np.abs(got[m] - want[m]).max() < 1e-12, (metric, dim)
+
+
+def test_pair_api_and_block_rows():
+    X = _profiles(130, 2500, "1111", seed=12)
+    assert phylodist.Eucl(X[0], X[1]) == pytest.approx(po.Eucl(X[0], X[1]), rel=2e-6)
+    assert phylodist.JSD(X[0], X[1]) == pytest.approx(po.JSD(X[0], X[1]), rel=2e-6)
+    assert phylodist.BC(X[0], X[1]) == pytest.approx(po.BC(X[0], X[1]), rel=2e-6)
+    assert phylodist.KT(X[0], X[1]) == pytest.approx(po.KT(X[0], X[1]), abs=1e-12)
+    assert phylodist.SC(X[0], X[1]) == pytest.approx(po.SC(X[0], X[1]), abs=1e-12)
+    # 2-D x 2-D JSD: rows index the second argument (core/phylodist.py:58-66)
+    X32 = X.astype(np.float32)
+    got = phylodist.JSD(X32, X32[10:31])
+    want = po.JSD(X32.astype(np.float64), X32[10:31].astype(np.float64))
+    assert got.shape == (21, 130) and got.dtype == np.float32
+    assert np.allclose(got, want, rtol=2e-6, atol=1e-9)
+    # block rows written at an offset, ragged edges (130 is not a multiple of 64)
+    Xd = torch.from_numpy(X32).cuda()
+    P, aux, dim = engine.prepare(Xd, "Eucl")
+    full = engine.distance_matrix_device(Xd, "Eucl", torch.float32, symmetric=False)
+    blk = torch.full((40, 130), -1.0, dtype=torch.float32, device="cuda")
+    engine.distance_block("Eucl", P, aux, dim, 70, 110, 0, 130, blk, 70, 0)
+    assert torch.equal(blk, full[70:110])
+
+
+def test_panel_streamer_matches_resident_matrix():
+    X = _profiles(300, 1500, "1111", seed=13, dtype=np.float32)
+    Xd = torch.from_numpy(X).cuda()
+    want = engine.distance_matrix_device(Xd, "JSD", torch.float32, symmetric=True).cpu().numpy()
+    for symmetric in (True, False):
+        got = np.zeros((300, 300), dtype=np.float32)
+        st = engine.PanelStreamer(Xd, "JSD", torch.float32, panel_rows=128, symmetric=symmetric)
+
+        def sink(r0, r1, host):
+            got[r0:r1] = host
+
+        st.run(sink)
+        assert np.array_equal(got, want)

@@ -1,0 +1,90 @@
+"""GPU parity: po_profile_batch (through the C ABI) against the reference golden
+vectors and the oracle.  Counts, totals and float64/float32 frequencies are bit exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_case_arrays
+from oracle import phylo_oracle as po
+from phyloligo_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _profile(seqs, pattern, strand):
+    res = engine.profile_sequences(seqs, pattern, strand, want=("counts", "totals", "freq64", "freq32"))
+    return {k: v.cpu().numpy() for k, v in res.items()}
+
+
+def test_golden_profiles_bit_exact(profile_golden):
+    seqs = profile_golden["sequences"]
+    groups = {}
+    for case in profile_golden["cases"]:
+        groups.setdefault((case["pattern"], case["strand"]), []).append(case)
+    for (pat, strand), cases in groups.items():
+        batch = [seqs[c["seq"]] for c in cases]
+        out = _profile(batch, pat, strand)
+        for r, c in enumerate(cases):
+            counts, total, freq = golden_case_arrays(c)
+            assert int(out["totals"][r]) == total, (pat, strand, c["seq"])
+            assert np.array_equal(out["counts"][r].astype(np.int64), counts), (pat, strand, c["seq"])
+            assert np.array_equal(out["freq64"][r], freq), (pat, strand, c["seq"])
+            assert np.array_equal(out["freq32"][r], freq.astype(np.float32))
+
+
+@pytest.mark.parametrize("pattern", ["1111", "11111", "111010011", "110101", "1" * 7, "1000000000000000001",
+                                     "11011000000000000000000000000011"])
+@pytest.mark.parametrize("strand", ["plus", "minus", "both"])
+def test_random_contigs_match_oracle(pattern, strand):
+    seqs = synth.make_sequences(40, 3000, seed=21) + [b"", b"NNNN", b"ACGT", b"acgtn" * 50]
+    out = _profile(seqs, pattern, strand)
+    for r, s in enumerate(seqs):
+        counts, total = po.count_vector_np(s, pattern, strand)
+        assert int(out["totals"][r]) == total
+        assert np.array_equal(out["counts"][r].astype(np.int64), counts)
+        assert np.array_equal(out["freq64"][r], po.frequency_np(s, pattern, strand))
+
+
+def test_fasta_text_with_line_breaks_and_long_contig():
+    # wrapped FASTA, CRLF, a record longer than one chunk sweep, empty record
+    seqs = synth.make_sequences(6, 60_000, seed=5) + [b""] + synth.make_sequences(3, 100, seed=6)
+    text = synth.to_fasta_bytes(seqs, line=60).replace(b"\n", b"\r\n", 7)
+    begin, end = engine.fasta_index(text)
+    assert len(begin) == len(seqs)
+    res = engine.profile_text(text, "1111", "both", want=("counts", "totals"), begin=begin, end=end)
+    counts = res["counts"].cpu().numpy()
+    for r, s in enumerate(seqs):
+        c, t = po.count_vector_np(s, "1111", "both")
+        assert np.array_equal(counts[r].astype(np.int64), c)
+        assert int(res["totals"][r].item()) == t
+
+
+def test_large_k_global_histogram():
+    seqs = synth.make_sequences(5, 5000, seed=8)
+    out = _profile(seqs, "1" * 9, "both")  # 4^9 bins: global-memory histogram path
+    for r, s in enumerate(seqs):
+        c, t = po.count_vector_np(s, "1" * 9, "both")
+        assert int(out["totals"][r]) == t
+        assert np.array_equal(out["counts"][r].astype(np.int64), c)
+
+
+def test_property_total_is_checksum_at_scale():
+    # size-independent property at a larger size: total == sum(counts) == windows in valid runs,
+    # both == plus + minus + junction (junction <= width-1 words)
+    text, nbases = synth.fast_fasta_bytes(2000, 20_000, seed=2)
+    begin, end = engine.fasta_index(text)
+    d_text = engine.text_to_device(text)
+    d_b = torch.from_numpy(begin).cuda()
+    d_e = torch.from_numpy(end).cuda()
+    outs = {s: engine.profile_device(d_text, d_b, d_e, "1111", s, want=("counts", "totals")) for s in ("plus", "minus", "both")}
+    for s in outs:
+        assert torch.equal(outs[s]["counts"].to(torch.int64).sum(dim=1), outs[s]["totals"])
+    assert torch.equal(outs["plus"]["totals"], outs["minus"]["totals"])
+    junction = outs["both"]["counts"] - outs["plus"]["counts"] - outs["minus"]["counts"]
+    assert int(junction.min().item()) >= 0 and int(junction.sum(dim=1).max().item()) <= 3
+    # minus counts are the reverse-complement permutation of plus counts for a contiguous k-mer
+    k = 4
+    idx = np.arange(4 ** k)
+    digits = [(idx >> (2 * j)) & 3 for j in range(k)]  # least significant first
+    rc = sum(((digits[j] ^ 1) << (2 * (k - 1 - j))) for j in range(k))
+    assert torch.equal(outs["minus"]["counts"], outs["plus"]["counts"][:, torch.from_numpy(rc).cuda()])

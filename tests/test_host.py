@@ -1,0 +1,124 @@
+"""CPU tests of the host layer: the C-ABI library loads and exports every declared
+symbol, pattern geometry, FASTA indexing, file formats, CLI surface, and the loud
+failure without a GPU (no compute calls are made here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import phylo_oracle as po
+from phyloligo_b200 import _lib, engine, io_formats, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "phyloligo_b200.h")).read()
+    declared = set(re.findall(r"\b(po_[a-z0-9_]+)\s*\(", header))
+    declared -= {"po_stream_t"}
+    assert declared == set(_lib.EXPORTED)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.po_version()
+
+
+def test_pattern_info_and_limits():
+    assert _lib.pattern_info("1111") == (4, 4, 256)
+    assert _lib.pattern_info("111010011") == (9, 6, 4096)
+    assert _lib.pattern_info("5") == (1, 0, 1)       # `-p 5` is the string "5": no '1' at all
+    assert _lib.pattern_info("100a1") == (5, 2, 16)  # anything but '1' is a don't-care position
+    with pytest.raises(_lib.PhyloligoError):
+        _lib.pattern_info("1" * 33)
+    with pytest.raises(_lib.PhyloligoError):
+        _lib.pattern_info("")
+    with pytest.raises(_lib.PhyloligoError):
+        _lib.pattern_info("1" * 11)
+
+
+def test_fasta_index_matches_oracle_reader(tmp_path):
+    seqs = synth.make_sequences(50, 700, seed=2) + [b"", b"ACGT"]
+    text = b"; stray text before the first header\n" + synth.to_fasta_bytes(seqs, line=70)
+    text = text.replace(b">c3\n", b">c3 some description > with a bracket\n")
+    path = tmp_path / "x.fa"
+    path.write_bytes(text)
+    begin, end = engine.fasta_index(text)
+    assert len(begin) == len(seqs)
+    want = list(po.read_fasta(str(path)))
+    got = [bytes(text[b:e]).replace(b"\n", b"").decode() for b, e in zip(begin, end)]
+    assert got == want == [s.decode() for s in seqs]
+    # no trailing newline, CRLF, multi-threaded scan on a larger buffer
+    big = synth.to_fasta_bytes(synth.make_sequences(3000, 600, seed=3))
+    b1, e1 = engine.fasta_index(big, threads=1)
+    b8, e8 = engine.fasta_index(big, threads=8)
+    assert np.array_equal(b1, b8) and np.array_equal(e1, e8) and len(b1) == 3000
+    b, e = engine.fasta_index(b">a\r\nAC\r\nGT\r\n>b\r\nTT")
+    assert b.tolist() == [4, 16] and e.tolist() == [12, 18]
+    assert engine.fasta_index(b"")[0].shape == (0,)
+
+
+def test_hdf5_and_memmap_formats(tmp_path):
+    a = np.random.default_rng(0).random((37, 19)).astype(np.float32)
+    p = str(tmp_path / "d.h5")
+    io_formats.write_hdf5(p, "distances", a)
+    assert np.array_equal(io_formats.read_hdf5(p, "distances"), a)
+    raw = open(p, "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and b"TREE" in raw and b"HEAP" in raw and b"SNOD" in raw
+    with pytest.raises(KeyError):
+        io_formats.read_hdf5(p, "frequencies")
+    with io_formats.Hdf5DatasetWriter(p, "frequencies", (10, 4), np.float64) as w:
+        for r in range(0, 10, 3):
+            w.write_rows(r, np.full((min(3, 10 - r), 4), float(r)))
+    got = io_formats.read_hdf5(p, "frequencies")
+    assert got.dtype == np.float64 and got[9, 0] == 9.0 and got[4, 3] == 3.0
+    m = np.arange(49, dtype=np.float32)
+    mp = str(tmp_path / "m.raw")
+    m.tofile(mp)
+    assert io_formats.read_memmap(mp).shape == (7, 7)
+    t = str(tmp_path / "t.txt")
+    io_formats.savetxt(t, a.astype(np.float64))
+    first = open(t).readline().split("\t")
+    assert len(first) == 19 and re.fullmatch(r"\d\.\d{18}e[+-]\d\d", first[0])
+    assert np.array_equal(io_formats.read_numpy(t), a.astype(np.float64))
+
+
+def test_cli_surface_matches_reference_flags():
+    from phyloligo_b200 import phyloligo
+    p = phyloligo.get_cmd(["-i", "x.fa", "--method", "joblib"])
+    assert p.pattern == 4 and p.strand == "both" and p.dist == "Eucl" and p.large == "None"
+    assert p.threads_max == 4 and p.out_file == "phyloligo.out" and p.freqchunksize == 250 and p.distchunksize == 250
+    assert os.path.isabs(p.workdir)
+    assert phyloligo.get_cmd(["-i", "x", "--method", "joblib", "-k", "5", "-p", "1101"]).pattern == "1101"
+    assert phyloligo.get_cmd(["-i", "x", "--method", "scoop", "-p", "1101", "-k", "5"]).pattern == 5
+    assert phyloligo.get_cmd(["-i", "x", "--method", "joblib", "-p", "5"]).pattern == "5"
+    with pytest.raises(SystemExit):
+        phyloligo.get_cmd(["-i", "x"])  # --method is required
+    with pytest.raises(SystemExit):
+        phyloligo.get_cmd(["-i", "x", "--method", "joblib", "-d", "XX"])
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu(tmp_path):
+    from phyloligo_b200 import phyloligo, phylodist
+    with pytest.raises(_lib.PhyloligoError):
+        phyloligo.compute_frequency("ACGTACGT", "11", "both")
+    with pytest.raises(_lib.PhyloligoError):
+        phylodist.JSD(np.ones(4) / 4, np.ones(4) / 4)
+    fa = tmp_path / "a.fa"
+    fa.write_bytes(b">a\nACGT\n")
+    with pytest.raises(_lib.PhyloligoError):
+        phyloligo.compute_frequencies("joblib", "None", str(fa), "11", "both", 250, 4, str(tmp_path))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "phyloligo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("phylo_oracle", "oracle") or f == "_none_", (dirpath, f)
