@@ -1,0 +1,481 @@
+#!/usr/bin/env python3
+"""Benchmark of the PhylOligo hot path on B200: profile a synthetic multi-FASTA and
+compute its all-by-all JSD matrix (BASELINE.json: contig-pairs/sec, JSD k=4, strand both).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--scale S]
+
+One "step" = one full pass over the workload: composition profiling of every
+contig (k=4, both strands) + the JSD distance matrix.  Default workload is
+BASELINE.json configs[1] (C2: 100 000 contigs x 20 kb); ``--scale`` shrinks the
+contig count for quick checks (the JSON line then says so).
+
+`value`: unique contig pairs N(N+1)/2 resolved per second with the FASTA text
+already resident in HBM and the matrix left in HBM.  `e2e`: the same pass from
+pinned HOST memory (FASTA bytes -> host index -> H2D -> kernels -> every row
+panel copied back D2H into pinned buffers), all inside the timed region.
+Multi-GPU (torchrun): records are sharded for profiling, profiles all-gathered
+over NCCL, row panels of the matrix assigned cyclically to ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "contig-pairs/sec (JSD, k=4)"
+UNIT = "pairs/s"
+PATTERN = "1111"
+STRAND = "both"
+DIM = 256
+JSD_FLOPS_PER_PAIR = 10 * DIM  # SURVEY.md 8(d) convention: 10 flop per dimension per pair
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the C2 contig count (1.0 = 100 000)")
+    ap.add_argument("--mean-len", type=int, default=20_000)
+    ap.add_argument("--panel-rows", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(n, mean_len):
+    return "C2: JSD k=4 strand=both, %d contigs x %d kb synthetic multi-FASTA" % (n, mean_len // 1000)
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    smax.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower() == "active":
+                        reasons.add(nm)
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------
+# CPU baselines (the oracle port; the only place bench.py executes oracle/)
+# ---------------------------------------------------------------------------
+def cpu_python_port_rates(seqs_sample, n_profile, n_dist, n_jobs):
+    """Time the Python restatement of the reference path the way the reference runs it
+    (joblib over sequences; sklearn.pairwise_distances with the callable metric,
+    bin/phyloligo.py:867-869, 388-390).  Returns (seconds per base, seconds per pair)."""
+    from joblib import Parallel, delayed
+    from sklearn.metrics import pairwise_distances
+    from oracle import phylo_oracle as po
+
+    prof = [s.decode("latin-1") for s in seqs_sample[:n_profile]]
+    t0 = time.perf_counter()
+    freqs = Parallel(n_jobs=n_jobs)(delayed(po.compute_frequency)(s, PATTERN, STRAND) for s in prof)
+    t_prof = time.perf_counter() - t0
+    bases = sum(len(s) for s in prof)
+    F = np.vstack([np.asarray(f, dtype=np.float64) for f in freqs])
+    if F.shape[0] < n_dist:  # cheap extra profiles for the distance sample
+        extra = [po.frequency_np(s, PATTERN, STRAND) for s in seqs_sample[F.shape[0]:n_dist]]
+        F = np.vstack([F] + extra) if extra else F
+    F = F[:n_dist]
+    t0 = time.perf_counter()
+    D = pairwise_distances(F, metric=po.JSD, n_jobs=n_jobs)
+    t_dist = time.perf_counter() - t0
+    n = F.shape[0]
+    evaluated = n * (n + 1) // 2 if n_jobs == 1 else n * n  # sklearn: triangle only when serial
+    assert D.shape == (n, n)
+    return t_prof / max(1, bases), t_dist / max(1, n * (n + 1) // 2), dict(
+        profile_contigs=len(prof), profile_bases=bases, profile_s=t_prof, dist_rows=n, dist_evaluations=evaluated,
+        dist_s=t_dist)
+
+
+def cpu_c_port_rates(seqs_sample, n_profile, n_dist, threads):
+    """The same sample through the multi-threaded C restatement (oracle/oracle.c)."""
+    from oracle import coracle
+    from phyloligo_b200 import engine
+
+    text, begin, end = engine.sequences_to_text(seqs_sample[:n_profile])
+    t0 = time.perf_counter()
+    F = coracle.profile_batch(text, begin, end, PATTERN, STRAND, threads=threads)
+    t_prof = time.perf_counter() - t0
+    bases = int((end - begin).sum())
+    F = F[:n_dist]
+    t0 = time.perf_counter()
+    coracle.pairwise_rows("JSD", F, threads=threads)
+    t_dist = time.perf_counter() - t0
+    n = F.shape[0]
+    return t_prof / max(1, bases), t_dist / max(1, n * n), dict(profile_bases=bases, profile_s=t_prof, dist_rows=n, dist_s=t_dist)
+
+
+def whole_job_pairs_per_s(n_contigs, total_bases, s_per_base, s_per_pair):
+    pairs = n_contigs * (n_contigs + 1) // 2
+    return pairs / (s_per_base * total_bases + s_per_pair * pairs)
+
+
+def sample_sequences(n, mean_len, seed=2):
+    from phyloligo_b200 import synth
+    return synth.make_sequences(n, mean_len, seed=seed)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (Python port of the joblib back-end,
+    all host cores) on a bounded sample of the same workload; the value is the
+    whole-job throughput those measured rates imply for the named workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_contigs = max(64, int(round(100_000 * args.scale)))
+    total_bases = n_contigs * args.mean_len
+    cores = os.cpu_count() or 1
+    n_profile = min(n_contigs, max(16, 2 * cores))
+    n_dist = min(n_contigs, 400)
+    seqs = sample_sequences(max(n_profile, n_dist), args.mean_len)
+    vals, detail = [], None
+    for it in range(args.warmup + args.steps):
+        spb, spp, detail = cpu_python_port_rates(seqs, n_profile, n_dist, cores)
+        if it >= args.warmup:
+            vals.append((spb, spp))
+    spb = float(np.mean([v[0] for v in vals]))
+    spp = float(np.mean([v[1] for v in vals]))
+    value = whole_job_pairs_per_s(n_contigs, total_bases, spb, spp)
+    step_ms = 1e3 * (detail["profile_s"] + detail["dist_s"])
+    sample = ("Python port of the reference joblib path, %d threads: %d contigs profiled, %d profiles all-pairs JSD "
+              "via sklearn.pairwise_distances(callable); value = whole-job pairs/s implied for the workload"
+              % (cores, n_profile, n_dist))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n_contigs, args.mean_len), "pattern": PATTERN, "strand": STRAND},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "seconds_per_base": spb, "seconds_per_pair": spp},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from phyloligo_b200 import _lib, engine, synth
+    from phyloligo_b200._lib import FLAG_MIRROR, FLAG_SKIP_LOWER
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+
+    n_contigs = max(64, int(round(100_000 * args.scale)))
+    fasta, total_bases = synth.fast_fasta_bytes(n_contigs, args.mean_len, seed=2)
+    pairs_unique = n_contigs * (n_contigs + 1) // 2
+
+    # ---- sharding: contiguous record ranges balanced by bytes; cyclic row panels ----
+    begin_all, end_all = engine.fasta_index(fasta)
+    assert begin_all.shape[0] == n_contigs
+    cum = np.cumsum(end_all - begin_all)
+    cuts = [int(np.searchsorted(cum, cum[-1] * r / world)) for r in range(world)] + [n_contigs]
+    cuts[0] = 0
+    rec_lo, rec_hi = cuts[rank], cuts[rank + 1]
+    n_local = rec_hi - rec_lo
+    n_max = max(cuts[r + 1] - cuts[r] for r in range(world))
+    # a shard starts at the '>' of its first record (= where the previous record's range ends)
+    byte_lo = (int(end_all[rec_lo - 1]) if rec_lo > 0 else 0) if n_local else 0
+    byte_hi = int(end_all[rec_hi - 1]) if n_local else 0
+    pinned_text = torch.from_numpy(fasta[byte_lo:byte_hi].copy()).pin_memory()
+    shard_bytes = byte_hi - byte_lo
+    panel = max(64, (args.panel_rows // 64) * 64)
+    n_panels = (n_contigs + panel - 1) // panel
+    my_panels = [p for p in range(n_panels) if p % world == rank]
+    symmetric = world == 1
+
+    # persistent device buffers
+    d_text = torch.empty(shard_bytes + 64, dtype=torch.uint8, device=device)
+    d_text[shard_bytes:].fill_(10)
+    d_text[:shard_bytes].copy_(pinned_text)
+    d_begin = torch.from_numpy(begin_all[rec_lo:rec_hi] - byte_lo).to(device)
+    d_end = torch.from_numpy(end_all[rec_lo:rec_hi] - byte_lo).to(device)
+    freq_pad = torch.zeros((n_max, DIM), dtype=torch.float32, device=device)
+    gathered = torch.empty((world * n_max, DIM), dtype=torch.float32, device=device) if world > 1 else None
+    if symmetric:
+        matrix = torch.empty((n_contigs, n_contigs), dtype=torch.float32, device=device)
+    else:
+        rows_owned = sum(min(n_contigs, (p + 1) * panel) - p * panel for p in my_panels)
+        matrix = torch.empty((max(1, rows_owned), n_contigs), dtype=torch.float32, device=device)
+    pin_ring = [torch.empty((panel, n_contigs), dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    pin_begin = torch.from_numpy(np.zeros(max(1, n_local), dtype=np.int64)).pin_memory()
+    pin_end = torch.from_numpy(np.zeros(max(1, n_local), dtype=np.int64)).pin_memory()
+
+    def profile_and_gather(b, e):
+        """profile this rank's records, return the full (n_contigs, DIM) float32 matrix"""
+        if n_local:
+            res = engine.profile_device(d_text, b, e, PATTERN, STRAND, want=("freq32",))
+            freq_pad[:n_local].copy_(res["freq32"])
+        if world == 1:
+            return freq_pad[:n_contigs]
+        dist.all_gather_into_tensor(gathered, freq_pad)
+        parts = [gathered[r * n_max: r * n_max + (cuts[r + 1] - cuts[r])] for r in range(world)]
+        return torch.cat(parts, dim=0)
+
+    def distance_panels(X, d2h):
+        """this rank's row panels; with d2h every finished panel is copied to pinned host memory"""
+        P, aux, dim = engine.prepare(X, "JSD")
+        d2h_bytes = 0
+        events = [None, None]
+        if symmetric and not d2h:
+            engine.distance_block("JSD", P, aux, dim, 0, n_contigs, 0, n_contigs, matrix, 0, 0,
+                                  FLAG_SKIP_LOWER | FLAG_MIRROR)
+            return 0
+        row_cursor = 0
+        for k, p in enumerate(my_panels):
+            r0, r1 = p * panel, min(n_contigs, (p + 1) * panel)
+            m = r1 - r0
+            if symmetric:
+                engine.distance_block("JSD", P, aux, dim, r0, r1, 0, n_contigs, matrix, 0, 0,
+                                      FLAG_SKIP_LOWER | FLAG_MIRROR)
+                src = matrix[r0:r1]
+            else:
+                src = matrix[row_cursor:row_cursor + m]
+                engine.distance_block("JSD", P, aux, dim, r0, r1, 0, n_contigs, src, r0, 0, 0)
+                row_cursor += m
+            if d2h:
+                ready = torch.cuda.Event()
+                ready.record()
+                slot = k & 1
+                if events[slot] is not None:
+                    events[slot].synchronize()  # the host consumer is done with this slot (discard sink)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ready)
+                    pin_ring[slot][:m].copy_(src, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    events[slot] = ev
+                d2h_bytes += m * n_contigs * 4
+        if d2h:
+            torch.cuda.current_stream().wait_stream(copy_stream)
+        return d2h_bytes
+
+    def step_resident():
+        X = profile_and_gather(d_begin, d_end)
+        distance_panels(X, d2h=False)
+
+    e2e_bytes = {"h2d": 0, "d2h": 0}
+
+    def step_e2e():
+        # host: index this rank's FASTA bytes; H2D: text + index; kernels; D2H: every panel
+        b, e = engine.fasta_index(pinned_text.numpy())
+        pin_begin[:len(b)].copy_(torch.from_numpy(b))
+        pin_end[:len(e)].copy_(torch.from_numpy(e))
+        d_text[:shard_bytes].copy_(pinned_text, non_blocking=True)
+        db = pin_begin[:len(b)].to(device, non_blocking=True)
+        de = pin_end[:len(e)].to(device, non_blocking=True)
+        X = profile_and_gather(db, de)
+        d2h = distance_panels(X, d2h=True)
+        e2e_bytes["h2d"] = shard_bytes + 16 * len(b)
+        e2e_bytes["d2h"] = d2h
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident measurement ----
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.timing_reset()
+    _lib.timing_enable(True)
+    launches0 = _lib.launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - launches0
+    _lib.timing_enable(False)
+    dist_ms, dist_n = _lib.timing_read(1)
+    prof_ms, prof_n = _lib.timing_read(0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = pairs_unique / (ms_per_step * 1e-3)
+
+    # ---- end to end (host buffers in, host buffers out) ----
+    for _ in range(max(1, min(2, args.warmup))):
+        step_e2e()
+    # CUDA events bracket the whole region: the host-side indexing shows up as stream idle time
+    e2e_s = torch.tensor([timed(step_e2e, args.steps) * 1e-3 / args.steps], dtype=torch.float64, device=device)
+    e2e_value = pairs_unique / float(e2e_s.item())
+    io_bytes = torch.tensor([e2e_bytes["h2d"], e2e_bytes["d2h"]], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(io_bytes, op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        # roofline of the dominant kernel (JSD tile kernel): algorithmic flop per launch / launch time
+        pairs_per_step_computed = 0
+        if symmetric:
+            for t0_ in range(0, n_contigs, 64):
+                pairs_per_step_computed += (min(n_contigs, t0_ + 64) - t0_) * (n_contigs - t0_)
+        else:
+            pairs_per_step_computed = sum((min(n_contigs, (p + 1) * panel) - p * panel) * n_contigs for p in my_panels)
+        launches_per_step = max(1, dist_n // max(1, args.steps))
+        avg_launch_ms = dist_ms / max(1, dist_n)
+        flop_per_launch = JSD_FLOPS_PER_PAIR * pairs_per_step_computed / launches_per_step
+        achieved = flop_per_launch / (avg_launch_ms * 1e-3) / 1e12 if avg_launch_ms > 0 else 0.0
+        fp32_peak = _lib.microbench(0)
+        mufu_peak = _lib.microbench(1)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        prof_bytes = shard_bytes + n_local * DIM * 4
+        prof_gbs = prof_bytes / (prof_ms / max(1, prof_n) * 1e-3) / 1e9 if prof_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": workload_name(n_contigs, args.mean_len), "pattern": PATTERN, "strand": STRAND,
+                "total_bases": total_bases, "unique_pairs": pairs_unique,
+                "pairs_computed_per_step_rank0": pairs_per_step_computed,
+                "parallelism": "1 GPU, upper triangle + mirror" if world == 1 else
+                               "%d ranks: records sharded, NCCL all-gather of profiles, cyclic row panels (full rows)" % world,
+                "l2": "inputs (%.2f GB text) and outputs (%.1f GB matrix) exceed the 126 MB L2; no flush needed"
+                      % (len(fasta) / 1e9, n_contigs * n_contigs * 4 / 1e9),
+                "e2e_sink": "row panels of %d rows copied D2H into a 2-slot pinned ring (discard sink)" % panel,
+            },
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                       "samples": clocks["samples"]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(io_bytes[0].item()),
+                    "d2h_bytes_per_step": int(io_bytes[1].item()), "ms_per_step": float(e2e_s.item()) * 1e3},
+            "gpu_launches": int(launches),
+            "roofline": {
+                "kernel": "distance_tile_kernel<JSD,float>", "bound": "fp32",
+                "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+                "peak_source": "po_microbench FFMA peak measured in this run (MEASURED_PEAKS.json has no FP32-pipe figure)",
+                "flop_convention": "10 flop per dimension per pair (SURVEY.md 8d); D=256",
+                "avg_launch_ms": avg_launch_ms, "launches_timed": int(dist_n),
+                "mufu_lg2_peak_Tops": mufu_peak,
+            },
+            "stages": {
+                "profiling_ms_per_launch": prof_ms / max(1, prof_n),
+                "profiling_gbases_per_s_rank0": (total_bases * (n_local / n_contigs)) / (prof_ms / max(1, prof_n) * 1e-3) / 1e9
+                if prof_ms > 0 else None,
+                "profiling_roofline": {"bound": "hbm", "achieved": prof_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                       "frac": prof_gbs / hbm_peak, "bytes": prof_bytes},
+                "distance_ms_per_step": dist_ms / max(1, args.steps),
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            seqs = sample_sequences(300, args.mean_len)
+            spb, spp, d1 = cpu_python_port_rates(seqs, 60, 300, 1)
+            cval = whole_job_pairs_per_s(n_contigs, total_bases, spb, spp)
+            cspb, cspp, d2 = cpu_c_port_rates(seqs, 300, 300, cores)
+            line["cpu_baseline"] = {
+                "value": cval, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": "Python port of the reference path on 1 core: 60 contigs profiled (%.1f s), 300 profiles "
+                          "all-pairs JSD (%.1f s); value = whole-job pairs/s those rates imply for this workload"
+                          % (d1["profile_s"], d1["dist_s"]),
+                "seconds_per_base": spb, "seconds_per_pair": spp,
+                "c_port": {"value": whole_job_pairs_per_s(n_contigs, total_bases, cspb, cspp), "unit": UNIT,
+                           "cores": cores, "note": "multi-threaded C restatement (oracle/oracle.c), same sample sizes x5"},
+            }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -108,7 +108,8 @@ int po_profile_batch(const uint8_t* d_text, const int64_t* d_begin, const int64_
 /*
  * Size in bytes of one prepared row for `metric` at profile dimension `dim`
  * (the operand layout po_distance_block consumes):
- *   Eucl / JSD / BC : dim rounded up to a multiple of 4, float32
+ *   Eucl / BC       : dim rounded up to a multiple of 4, float32
+ *   JSD             : dim rounded up to a multiple of 32, float32 (zeros biased to 1e-30)
  *   SC              : the same count of int32 (centred doubled average ranks)
  *   KT              : packed order-relation bit masks, 2 * ceil(dim(dim-1)/2 / 128) * 16 bytes
  */
@@ -163,6 +164,10 @@ int64_t po_launch_count(void);
 int po_timing_enable(int on);
 int po_timing_reset(void);
 int po_timing_read(int family, double* total_ms, int64_t* launches);
+
+/* Pipe-peak microbenchmark for roofline denominators that MEASURED_PEAKS.json lacks.
+ * kind 0: FP32 FFMA TFLOP/s, 1: MUFU.LG2 1e12 op/s, 2: POPC 1e12 op/s (best of 4 timed runs). */
+int po_microbench(int kind, double* result);
 
 #ifdef __cplusplus
 }

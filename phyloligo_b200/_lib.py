@@ -23,7 +23,7 @@ TILE = 64
 EXPORTED = [
     "po_version", "po_last_error", "po_device_info", "po_pattern_info", "po_fasta_index_host",
     "po_profile_batch", "po_prepared_row_bytes", "po_prepare_profiles", "po_distance_block",
-    "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read",
+    "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read", "po_microbench",
 ]
 
 
@@ -70,6 +70,8 @@ def load():
     lib.po_timing_reset.restype = i32
     lib.po_timing_read.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(i64)]
     lib.po_timing_read.restype = i32
+    lib.po_microbench.argtypes = [i32, C.POINTER(C.c_double)]
+    lib.po_microbench.restype = i32
     _lib = lib
     return lib
 
@@ -105,3 +107,10 @@ def timing_read(family: int):
     ms, n = C.c_double(), C.c_int64()
     check(load().po_timing_read(family, C.byref(ms), C.byref(n)), "po_timing_read")
     return ms.value, n.value
+
+
+def microbench(kind: int) -> float:
+    """0: FP32 FFMA TFLOP/s, 1: MUFU.LG2 1e12 op/s, 2: POPC 1e12 op/s."""
+    out = C.c_double()
+    check(load().po_microbench(kind, C.byref(out)), "po_microbench")
+    return out.value

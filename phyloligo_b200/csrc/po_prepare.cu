@@ -1,6 +1,10 @@
 // Per-row operand preparation for the distance tiles (sm_100a).
 //
-//   Eucl / JSD : float32 copy of the profile, zero padded to a multiple of 4.
+//   Eucl       : float32 copy of the profile, zero padded to a multiple of 4.
+//   JSD        : the same copy plus 1e-30: exact zeros (and the padding) become 1e-30
+//                while every representable frequency (>= 1e-22) is unchanged, so the
+//                tile kernel's a+b is never 0 and needs no clamp; the 1e-30 entries
+//                change a term by < 1e-27 relative.
 //   BC         : the same copy; aux = sum of the row (the sum|a+b| denominator of
 //                scipy's braycurtis splits into row sums for non-negative profiles;
 //                a negative entry poisons aux with NaN so the result is loudly NaN).
@@ -25,6 +29,9 @@ int64_t prepared_row_elems(int metric, int64_t dim) {
         const int64_t groups = (nbits + 127) / 128;  // 4 words of 32 bits per group
         return (groups > 0 ? groups : 1) * 8;
     }
+    // JSD rows are padded (with the 1e-30 bias) to a whole 32-element pipeline chunk so
+    // the tile kernel never meets a zero-filled (a = b = 0) lane
+    if (metric == PO_JSD) return (dim + 31) / 32 * 32;
     return (dim + 3) / 4 * 4;
 }
 
@@ -36,7 +43,7 @@ __device__ __forceinline__ double load_as_double(const void* X, int64_t idx) {
 template <typename T>
 __global__ void __launch_bounds__(256) prepare_copy_kernel(const void* __restrict__ X, int64_t n, int64_t dim,
                                                            int64_t ldx, float* __restrict__ P, int64_t ldp,
-                                                           double* __restrict__ aux, int want_sum) {
+                                                           double* __restrict__ aux, int want_sum, float bias) {
     const int64_t row = blockIdx.x;
     double s = 0.0;
     bool neg = false;
@@ -48,7 +55,7 @@ __global__ void __launch_bounds__(256) prepare_copy_kernel(const void* __restric
             s += (double)v;
             neg |= (v < 0.f);
         }
-        P[row * ldp + e] = v;
+        P[row * ldp + e] = v + bias;
     }
     if (want_sum) {
         __shared__ double red[8];
@@ -160,7 +167,8 @@ static int launch_prepare_t(int metric, const void* d_X, int64_t n, int64_t dim,
                 set_error("BC needs d_aux");
                 return PO_ERR_ARG;
             }
-            prepare_copy_kernel<T><<<grid, 256, 0, stream>>>(d_X, n, dim, ldx, (float*)d_P, ldp, d_aux, want_sum);
+            const float bias = (metric == PO_JSD) ? 1e-30f : 0.0f;
+            prepare_copy_kernel<T><<<grid, 256, 0, stream>>>(d_X, n, dim, ldx, (float*)d_P, ldp, d_aux, want_sum, bias);
             count_launch(2);
             PO_LAUNCH_CHECK("prepare_copy_kernel");
             return PO_OK;
