@@ -106,19 +106,25 @@ int po_profile_batch(const uint8_t* d_text, const int64_t* d_begin, const int64_
                      double* d_freq64, float* d_freq32, po_stream_t stream);
 
 /*
- * Size in bytes of one prepared row for `metric` at profile dimension `dim`
- * (the operand layout po_distance_block consumes):
- *   Eucl / BC       : dim rounded up to a multiple of 4, float32
- *   JSD             : dim rounded up to a multiple of 32, float32 (zeros biased to 1e-30)
- *   SC              : the same count of int32 (centred doubled average ranks)
- *   KT              : packed order-relation bit masks, 2 * ceil(dim(dim-1)/2 / 128) * 16 bytes
+ * Size in bytes of the prepared operand buffer (the layout po_distance_block consumes)
+ * of n profiles of dimension `dim` for `metric`; the caller allocates it.
+ *   Eucl / BC : n rows of dim rounded up to a multiple of 4, float32
+ *   SC        : the same count of int32 (centred doubled average ranks)
+ *   KT        : n rows of packed order-relation bit masks, 2 * ceil(dim(dim-1)/2 / 128) * 16 bytes
+ *   JSD       : float32 with exact zeros biased to 1e-30, dim rounded up to a multiple of 32
+ *               and n to a multiple of 64, stored as bulk-copy blocks: [n/64][dim/32] blocks
+ *               of [32 dims][64 profiles], then [n/32][dim/32] blocks of
+ *               [32 dims][32 profiles][2] (every value twice, for packed f32x2 math)
+ * po_prepared_row_bytes is the per-profile figure (exact for every metric but JSD,
+ * whose buffer is padded to whole groups of 64 profiles).
  */
+int64_t po_prepared_bytes(int metric, int64_t n, int64_t dim);
 int64_t po_prepared_row_bytes(int metric, int64_t dim);
 
 /*
  * Prepare the operand matrix for a metric from raw profiles.
  *   d_X       [n x ldx] profiles, float32 or float64 (`dtype`), ldx in elements
- *   d_P       [n x po_prepared_row_bytes] prepared rows (written)
+ *   d_P       po_prepared_bytes(metric, n, dim) bytes of prepared operands (written), 16-byte aligned
  *   d_aux     [n] float64 per-row constant (written):
  *               SC: sum of squares of the centred doubled ranks (0 = constant row)
  *               KT: number of element pairs that are not tied in the row

@@ -22,7 +22,7 @@ TILE = 64
 # every symbol include/phyloligo_b200.h declares (tests check the library exports them all)
 EXPORTED = [
     "po_version", "po_last_error", "po_device_info", "po_pattern_info", "po_fasta_index_host",
-    "po_profile_batch", "po_prepared_row_bytes", "po_prepare_profiles", "po_distance_block",
+    "po_profile_batch", "po_prepared_row_bytes", "po_prepared_bytes", "po_prepare_profiles", "po_distance_block",
     "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read", "po_microbench",
 ]
 
@@ -60,6 +60,8 @@ def load():
     lib.po_profile_batch.restype = i32
     lib.po_prepared_row_bytes.argtypes = [i32, i64]
     lib.po_prepared_row_bytes.restype = i64
+    lib.po_prepared_bytes.argtypes = [i32, i64, i64]
+    lib.po_prepared_bytes.restype = i64
     lib.po_prepare_profiles.argtypes = [i32, vp, i32, i64, i64, i64, vp, vp, vp]
     lib.po_prepare_profiles.restype = i32
     lib.po_distance_block.argtypes = [i32, vp, vp, i64, i64, i64, i64, i64, i64, vp, i64, i64, i64, i32, u32, vp]

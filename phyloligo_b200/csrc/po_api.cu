@@ -198,7 +198,15 @@ int64_t po_prepared_row_bytes(int metric, int64_t dim) {
         set_error("po_prepared_row_bytes: bad metric/dim");
         return PO_ERR_ARG;
     }
-    return prepared_row_elems(metric, dim) * 4;
+    return prepared_row_elems(metric, dim) * 4 * (metric == PO_JSD ? 3 : 1);
+}
+
+int64_t po_prepared_bytes(int metric, int64_t n, int64_t dim) {
+    if (metric < PO_EUCL || metric > PO_SC || dim < 1 || n < 0) {
+        set_error("po_prepared_bytes: bad metric/n/dim");
+        return PO_ERR_ARG;
+    }
+    return prepared_bytes(metric, n, dim);
 }
 
 int po_prepare_profiles(int metric, const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx,

@@ -1,30 +1,16 @@
-// All-by-all distance tiles on sm_100a CUDA cores: Eucl, JSD, BC, SC, KT.
+// All-by-all distance tiles on sm_100a CUDA cores: Eucl, BC, SC, KT (JSD lives in po_jsd.cu).
 //
-// Replaces phylodist.Eucl/JSD/KT/BC/SC (reference core/phylodist.py:36-85) and the
+// Replaces phylodist.Eucl/KT/BC/SC (reference core/phylodist.py:36-41, 71-85) and the
 // block-row slice workers *_loc / *_h5py (bin/phyloligo.py:195-301).
 //
-// One CTA computes a TM x 64 tile of the matrix (TM = 64 rows with 256 threads, or
-// TM = 32 rows with 128 threads -- four such CTAs share an SM and cover for each other
-// at the chunk barrier).  Thread (ty, tx) owns the 4 x 4 pairs (rows ty + (TM/4) i,
-// cols tx + 16 j).  Operand rows are "prepared
-// rows" of 32-bit elements (po_prepare_profiles): float32 profiles (Eucl, JSD,
-// BC), int32 centred doubled ranks (SC) or packed order-relation bit masks (KT).
-// The K dimension is streamed in chunks of 32 elements through a double-buffered
-// cp.async pipeline into shared memory with a row pitch of 36 words, which makes
-// the strided 128-bit operand reads bank-conflict free.  Partial sums are kept
-// in float32 for one chunk (32 non-negative terms) and folded into float64 (or
-// int64) accumulators per chunk, so the result carries no long-sum rounding.
-//
-// JSD.  The reference computes 0.5*sum(a ln(a/h) + b ln(b/h)), h = (a+b)/2, in
-// nats with 0*ln0 := 0.  Per dimension this kernel evaluates the identical
-// quantity in a cancellation-free form.  With s = a+b, d = a-b, x = d/s, u = x^2:
-//     a ln(a/h) + b ln(b/h) = (s/2) * f(x),   f(x) = (1+x)ln(1+x) + (1-x)ln(1-x) >= 0
-//     f(x) = u * G(u),  G(u) = sum_{n>=1} u^(n-1) / (n(2n-1))        (u <= 1/2)
-//     f(x) = E(w) + w ln w,  w = 1-|x| = 2 min(a,b)/s, E(w)=(2-w)ln(2-w)  (u > 1/2)
-// Every term is >= 0, so the sum has no cancellation; G and E are polynomial fits
-// at float32 rounding level (tools/jsd_poly_fit.py) and the only transcendental is
-// one MUFU.LG2 whose argument is < 0.15, where its error is relative (2 ulp).
-// No fast-math flags are used; the a = b = 0 case yields exactly 0.
+// One CTA (256 threads) computes a 64 x 64 tile of the matrix.  Thread (ty, tx) owns the
+// 4 x 4 pairs (rows ty + 16 i, cols tx + 16 j).  Operand rows are "prepared rows" of 32-bit
+// elements (po_prepare_profiles): float32 profiles (Eucl, BC), int32 centred doubled ranks
+// (SC) or packed order-relation bit masks (KT).  The K dimension is streamed in chunks of 32
+// elements through a double-buffered cp.async pipeline into shared memory with a row pitch
+// of 36 words, which makes the strided 128-bit operand reads bank-conflict free.  Partial
+// sums are kept in float32 for one chunk (32 non-negative terms) and folded into float64
+// (or int64) accumulators per chunk, so the result carries no long-sum rounding.
 #include <stdlib.h>
 #include "po_common.cuh"
 
@@ -35,118 +21,16 @@ constexpr int DK = 32;          // K elements per pipeline stage
 constexpr int PITCH = DK + 4;   // smem row pitch in words
 constexpr int NTHREADS = 256;
 
-enum Kind { K_EUCL = 0, K_JSD = 1, K_KT = 2, K_BC = 3, K_SC = 4 };
+enum Kind { K_EUCL = 0, K_KT = 2, K_BC = 3, K_SC = 4 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     int sz = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gsrc), "r"(sz));
 }
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// .ftz forms: a single MUFU each (the non-ftz forms add denormal range handling).
-// Their arguments here are never denormal: see the operand bias in po_prepare.cu.
-__device__ __forceinline__ float lg2_approx(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// ---- per-dimension JSD term pieces; a term is s * f(x) = 4 * (its contribution to JSD) ----
-// Operands carry a +1e-30 bias on exact zeros (po_prepare.cu), so s >= 2e-30 and
-// min(a,b)/s >= 5e-31 need no clamping; a = b gives d = 0 and the term is exactly 0.
-
-// regime A factor G(u), u = x^2 in [0, 1/2] (degree 7)
-__device__ __forceinline__ float jsd_G(float u) {
-    float G = 5.809747504e-02f;
-    G = fmaf(G, u, -4.418099709e-02f);
-    G = fmaf(G, u, 4.228754936e-02f);
-    G = fmaf(G, u, 1.528030711e-02f);
-    G = fmaf(G, u, 3.664686569e-02f);
-    G = fmaf(G, u, 6.660644403e-02f);
-    G = fmaf(G, u, 1.666681249e-01f);
-    G = fmaf(G, u, 9.999999943e-01f);
-    return G;
-}
-// regime B value f = E(w) + w ln w with v = w/2 = min(a,b)/s in [0, 0.1465]
-__device__ __forceinline__ float jsd_fB(float v) {
-    //   E(2v) + 2 ln2 * v  folded into one polynomial in v (degree 4)
-    float E = 2.100300184e-01f;                 // 16 * 1.312687615e-02
-    E = fmaf(E, v, 3.274813073e-01f);           //  8 * 4.093516341e-02
-    E = fmaf(E, v, 1.000313256e+00f);           //  4 * 2.500783139e-01
-    E = fmaf(E, v, -2.000005795e+00f);          //  2 * -1.693150078 + 2 ln 2
-    E = fmaf(E, v, 1.386294378e+00f);
-    const float vl = v * 1.386294361f;          // 2 ln2 * v
-    return fmaf(vl, lg2_approx(v), E);          // = E(w) + w ln w
-}
-
-// One dimension of a 4 x 4 pair block, both regimes evaluated for every term ("unified"):
-// best when large-ratio terms are common (sparse high-dimensional profiles).
-__device__ __forceinline__ void jsd_dim_unified(const float (&a)[4], const float (&b)[4], float (&c)[4][4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float s = a[i] + b[j];
-            const float d = a[i] - b[j];
-            const float rs = rcp_approx(s);  // MUFU.RCP, 1 ulp
-            const float x = d * rs;
-            const float u = x * x;
-            const bool regB = u > 0.5f;
-            const float fB = jsd_fB(fminf(a[i], b[j]) * rs);
-            const float G = jsd_G(u);
-            c[i][j] = fmaf(regB ? s : d * x, regB ? fB : G, c[i][j]);
-        }
-}
-
-// The same dimension in two phases ("split").  Phase 1 adds the series value
-// q * G(u) for every term and only tracks the largest u it met (one FMNMX per term,
-// no predicates).  If some lane of the warp met u > 1/2 in this dimension, phase 2
-// revisits the 16 terms and, for exactly those with u > 1/2, swaps the series value
-// for the log-based one: c += s*fB - q*G(u) (G's polynomial is finite on [0, 1], so
-// the provisional value is harmless).  On composition profiles of real contigs a warp
-// needs phase 2 for roughly one dimension in ten.  The result of a pair depends only
-// on that pair's data, never on the votes of its neighbours.
-__device__ __forceinline__ void jsd_dim_split(const float (&a)[4], const float (&b)[4], float (&c)[4][4]) {
-    float umax = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float d = a[i] - b[j];
-            const float x = d * rcp_approx(a[i] + b[j]);
-            const float u = x * x;
-            umax = fmaxf(umax, u);
-            c[i][j] = fmaf(d * x, jsd_G(u), c[i][j]);
-        }
-    if (__any_sync(0xFFFFFFFFu, umax > 0.5f)) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float s = a[i] + b[j];
-                const float d = a[i] - b[j];
-                const float rs = rcp_approx(s);
-                const float x = d * rs;
-                const float u = x * x;
-                if (u > 0.5f) {
-                    const float wrong = (d * x) * jsd_G(u);
-                    c[i][j] += fmaf(s, jsd_fB(fminf(a[i], b[j]) * rs), -wrong);
-                }
-            }
-    }
-}
 
 template <int KIND>
 struct Accum {};
@@ -172,26 +56,6 @@ struct Accum<K_EUCL> {
             for (int j = 0; j < 4; ++j) { t[i][j] += (double)c[i][j]; c[i][j] = 0.f; }
     }
     __device__ __forceinline__ double result(int i, int j, double, double) const { return sqrt(t[i][j]); }
-};
-
-template <>
-struct Accum<K_JSD> {
-    float c[4][4];
-    double t[4][4];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { c[i][j] = 0.f; t[i][j] = 0.0; }
-    }
-    __device__ __forceinline__ void term(int, int, float, float) {}  // JSD uses jsd_dim_* directly
-    __device__ __forceinline__ void fold() {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { t[i][j] += (double)c[i][j]; c[i][j] = 0.f; }
-    }
-    __device__ __forceinline__ double result(int i, int j, double, double) const { return 0.25 * t[i][j]; }
 };
 
 template <>
@@ -273,17 +137,13 @@ struct TileParams {
     int kdim;             // number of elements to stream (== ldp)
 };
 
-// VARIANT is used by JSD only: 0 = split (two-phase), 1 = unified.
-// TM = tile rows (32 or 64); tile columns are always 64; threads = 4 * TM.
-template <int KIND, typename OUT_T, int VARIANT, int TM>
-__global__ void __launch_bounds__(4 * TM, TM == 32 ? 4 : 2) distance_tile_kernel(const TileParams p) {
+// TM = tile rows; tile columns are always 64; threads = 4 * TM.
+template <int KIND, typename OUT_T, int TM>
+__global__ void __launch_bounds__(4 * TM, 2) distance_tile_kernel(const TileParams p) {
     constexpr int NT = 4 * TM;          // threads
     constexpr int RS = TM / 4;          // row stride between the 4 rows a thread owns
     constexpr int TN = TILE;            // 64 columns
-    // JSD walks one dimension per iteration with scalar shared-memory reads: pitch 33
-    // makes those conflict free (bank = row + d); the other kinds read 128-bit groups
-    // at pitch 36.
-    constexpr int SP = (KIND == K_JSD) ? (DK + 1) : PITCH;
+    constexpr int SP = PITCH;
     constexpr int STAGE_WORDS = (TM + TN) * PITCH;
     constexpr int TP = TN + 1;          // pitch of the output staging tile
     constexpr int SMEM_WORDS = (2 * STAGE_WORDS * 4 > (int)sizeof(OUT_T) * TM * TP)
@@ -298,24 +158,14 @@ __global__ void __launch_bounds__(4 * TM, TM == 32 ? 4 : 2) distance_tile_kernel
 
     const int64_t nlast = p.n - 1;
     const int nchunks = (p.kdim + DK - 1) / DK;
-    const int wrow = tid >> 5, lane = tid & 31;  // JSD loader: lane <-> dimension
     const int lrow = tid >> 3, lc4 = tid & 7;    // 128-bit loader: 8 float4 per row
-    constexpr int NWARP = NT / 32, LROWS = NT / 8;
+    constexpr int LROWS = NT / 8;
 
     auto issue = [&](int chunk, int stage) {
         uint32_t* sA = smem + stage * STAGE_WORDS;
         uint32_t* sB = sA + TM * PITCH;
         const int k0 = chunk * DK;
-        if constexpr (KIND == K_JSD) {
-            // 32-bit copies (pitch-33 rows are not 16-byte aligned); kdim is a whole number
-            // of chunks for JSD (rows are padded with the bias)
-#pragma unroll
-            for (int r = wrow; r < TM; r += NWARP)
-                cp_async4(sA + r * SP + lane, p.P + min(row_base + r, nlast) * p.ldp + k0 + lane);
-#pragma unroll
-            for (int r = wrow; r < TN; r += NWARP)
-                cp_async4(sB + r * SP + lane, p.P + min(col_base + r, nlast) * p.ldp + k0 + lane);
-        } else {
+        {
             const bool ok = (k0 + lc4 * 4) < p.kdim;
 #pragma unroll
             for (int r = lrow; r < TM; r += LROWS)
@@ -342,34 +192,7 @@ __global__ void __launch_bounds__(4 * TM, TM == 32 ? 4 : 2) distance_tile_kernel
         __syncthreads();
         const uint32_t* sA = smem + stage * STAGE_WORDS;
         const uint32_t* sB = sA + TM * PITCH;
-        if constexpr (KIND == K_JSD) {
-            // software pipelined: the operands of dimension d+1 are read while d computes.
-            // One base pointer per operand; the 4 rows are constant offsets from it.  The
-            // prefetch of "dimension 32" reads the pad column of the pitch-33 row (unused).
-            const float* pa = reinterpret_cast<const float*>(sA) + ty * SP;
-            const float* pb = reinterpret_cast<const float*>(sB) + tx * SP;
-            float a[4], b[4], an[4], bn[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                a[i] = pa[RS * i * SP];
-                b[i] = pb[16 * i * SP];
-            }
-#pragma unroll 2
-            for (int d = 0; d < DK; ++d) {
-                ++pa;
-                ++pb;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    an[i] = pa[RS * i * SP];
-                    bn[i] = pb[16 * i * SP];
-                }
-                if constexpr (VARIANT == 0) jsd_dim_split(a, b, acc.c);
-                else jsd_dim_unified(a, b, acc.c);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { a[i] = an[i]; b[i] = bn[i]; }
-            }
-            acc.fold();
-        } else if constexpr (KIND == K_KT) {
+        if constexpr (KIND == K_KT) {
             // elements come in groups of 8 words: 4 "up" masks then 4 "down" masks
 #pragma unroll
             for (int g8 = 0; g8 < DK / 8; ++g8) {
@@ -452,7 +275,7 @@ __global__ void __launch_bounds__(4 * TM, TM == 32 ? 4 : 2) distance_tile_kernel
     }
 }
 
-template <int KIND, int VARIANT, int TM>
+template <int KIND, int TM>
 static int launch_kind(const TileParams& p, int out_dtype, cudaStream_t stream) {
     const int64_t tr = (p.row1 - p.row0 + TM - 1) / TM, tc = (p.col1 - p.col0 + TILE - 1) / TILE;
     if (tr > 65535) {
@@ -462,28 +285,12 @@ static int launch_kind(const TileParams& p, int out_dtype, cudaStream_t stream) 
     dim3 grid((unsigned)tc, (unsigned)tr, 1);
     LaunchTimer t(1, stream);
     if (out_dtype == PO_F32)
-        distance_tile_kernel<KIND, float, VARIANT, TM><<<grid, 4 * TM, 0, stream>>>(p);
+        distance_tile_kernel<KIND, float, TM><<<grid, 4 * TM, 0, stream>>>(p);
     else
-        distance_tile_kernel<KIND, double, VARIANT, TM><<<grid, 4 * TM, 0, stream>>>(p);
+        distance_tile_kernel<KIND, double, TM><<<grid, 4 * TM, 0, stream>>>(p);
     count_launch(1);
     PO_LAUNCH_CHECK("distance_tile_kernel");
     return PO_OK;
-}
-
-// JSD variant: the two-phase kernel pays off while large-ratio terms are rare, which
-// holds for dense profiles (4^k <= 1024 bins on kb-sized contigs); sparse
-// high-dimensional profiles take the unified kernel.  PO_JSD_VARIANT=split|unified
-// overrides the choice (used by the parity tests to cover both).
-static int jsd_variant(int64_t dim) {
-    const char* e = getenv("PO_JSD_VARIANT");
-    if (e && !strcmp(e, "split")) return 0;
-    if (e && !strcmp(e, "unified")) return 1;
-    return dim <= 1024 ? 0 : 1;
-}
-static int jsd_tile_rows() {
-    const char* e = getenv("PO_JSD_TM");
-    if (e && !strcmp(e, "64")) return 64;
-    return 32;
 }
 
 int launch_distance(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim,
@@ -501,17 +308,13 @@ int launch_distance(int metric, const void* d_P, const double* d_aux, int64_t n,
     p.out = d_out; p.ld_out = ld_out; p.out_row0 = out_row0; p.out_col0 = out_col0;
     p.flags = flags;
     switch (metric) {
-        case PO_EUCL: return launch_kind<K_EUCL, 0, 64>(p, out_dtype, stream);
-        case PO_JSD: {
-            const int v = jsd_variant(dim), tm = jsd_tile_rows();
-            if (v == 0) return tm == 32 ? launch_kind<K_JSD, 0, 32>(p, out_dtype, stream)
-                                        : launch_kind<K_JSD, 0, 64>(p, out_dtype, stream);
-            return tm == 32 ? launch_kind<K_JSD, 1, 32>(p, out_dtype, stream)
-                            : launch_kind<K_JSD, 1, 64>(p, out_dtype, stream);
-        }
-        case PO_BC: return launch_kind<K_BC, 0, 64>(p, out_dtype, stream);
-        case PO_SC: return launch_kind<K_SC, 0, 64>(p, out_dtype, stream);
-        case PO_KT: return launch_kind<K_KT, 0, 64>(p, out_dtype, stream);
+        case PO_EUCL: return launch_kind<K_EUCL, 64>(p, out_dtype, stream);
+        case PO_JSD:
+            return launch_jsd(d_P, n, dim, row0, row1, col0, col1, d_out, ld_out, out_row0, out_col0, out_dtype,
+                              flags, stream);
+        case PO_BC: return launch_kind<K_BC, 64>(p, out_dtype, stream);
+        case PO_SC: return launch_kind<K_SC, 64>(p, out_dtype, stream);
+        case PO_KT: return launch_kind<K_KT, 64>(p, out_dtype, stream);
     }
     set_error("unknown metric %d", metric);
     return PO_ERR_ARG;

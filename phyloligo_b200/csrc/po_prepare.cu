@@ -1,10 +1,13 @@
 // Per-row operand preparation for the distance tiles (sm_100a).
 //
 //   Eucl       : float32 copy of the profile, zero padded to a multiple of 4.
-//   JSD        : the same copy plus 1e-30: exact zeros (and the padding) become 1e-30
+//   JSD        : float32 copy plus 1e-30: exact zeros (and the padding) become 1e-30
 //                while every representable frequency (>= 1e-22) is unchanged, so the
 //                tile kernel's a+b is never 0 and needs no clamp; the 1e-30 entries
-//                change a term by < 1e-27 relative.
+//                change a term by < 1e-27 relative.  Stored "blocked" for the bulk
+//                copies of po_jsd.cu: [n/64][dim/32] blocks of [32 dims][64 profiles]
+//                (column operand) followed by [n/32][dim/32] blocks of
+//                [32 dims][32 profiles][2] with every value twice (row operand).
 //   BC         : the same copy; aux = sum of the row (the sum|a+b| denominator of
 //                scipy's braycurtis splits into row sums for non-negative profiles;
 //                a negative entry poisons aux with NaN so the result is loudly NaN).
@@ -33,6 +36,13 @@ int64_t prepared_row_elems(int metric, int64_t dim) {
     // the tile kernel never meets a zero-filled (a = b = 0) lane
     if (metric == PO_JSD) return (dim + 31) / 32 * 32;
     return (dim + 3) / 4 * 4;
+}
+
+// total bytes of the prepared operand buffer of n rows
+int64_t prepared_bytes(int metric, int64_t n, int64_t dim) {
+    const int64_t ldp = prepared_row_elems(metric, dim);
+    if (metric == PO_JSD) return 3 * ((n + 63) / 64 * 64) * ldp * 4;  // blocked B + doubled A, rows padded to 64
+    return n * ldp * 4;
 }
 
 template <typename T>
@@ -71,6 +81,37 @@ __global__ void __launch_bounds__(256) prepare_copy_kernel(const void* __restric
             double t = 0.0;
             for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
             aux[row] = sneg ? __longlong_as_double(0x7FF8000000000000ll) : t;
+        }
+    }
+}
+
+
+// JSD: biased float32 profiles in the blocked layout of po_jsd.cu.  One CTA per
+// (group of 64 profiles, chunk of 32 dimensions); the transpose goes through shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) prepare_jsd_kernel(const void* __restrict__ X, int64_t n, int64_t dim,
+                                                          int64_t ldx, float* __restrict__ PB, float* __restrict__ PA,
+                                                          int nchunks) {
+    __shared__ float tile[64][33];
+    const int64_t grp = blockIdx.x;
+    const int kc = blockIdx.y;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int r = w; r < 64; r += 8) {
+        const int64_t row = grp * 64 + r;
+        const int64_t e = (int64_t)kc * 32 + lane;
+        float v = 0.f;
+        if (row < n && e < dim) v = (float)load_as_double<T>(X, row * ldx + e);
+        tile[r][lane] = v + 1e-30f;
+    }
+    __syncthreads();
+    float* blkB = PB + ((size_t)grp * nchunks + kc) * 2048;
+    for (int e = threadIdx.x; e < 2048; e += 256) blkB[e] = tile[e & 63][e >> 6];  // [d][c]
+    // two row-operand blocks (profiles 0..31 and 32..63 of the group): [d][r][2]
+    for (int h = 0; h < 2; ++h) {
+        float2* blkA = reinterpret_cast<float2*>(PA + ((size_t)(grp * 2 + h) * nchunks + kc) * 2048);
+        for (int e = threadIdx.x; e < 1024; e += 256) {
+            const float v = tile[h * 32 + (e & 31)][e >> 5];
+            blkA[e] = make_float2(v, v);
         }
     }
 }
@@ -159,16 +200,25 @@ static int launch_prepare_t(int metric, const void* d_X, int64_t n, int64_t dim,
     const int64_t ldp = prepared_row_elems(metric, dim);
     const unsigned grid = (unsigned)n;
     switch (metric) {
+        case PO_JSD: {
+            const int nchunks = (int)(ldp / 32);
+            const int64_t npad = (n + 63) / 64 * 64;
+            float* PB = (float*)d_P;
+            float* PA = PB + npad * ldp;
+            dim3 g((unsigned)(npad / 64), (unsigned)nchunks, 1);
+            prepare_jsd_kernel<T><<<g, 256, 0, stream>>>(d_X, n, dim, ldx, PB, PA, nchunks);
+            count_launch(2);
+            PO_LAUNCH_CHECK("prepare_jsd_kernel");
+            return PO_OK;
+        }
         case PO_EUCL:
-        case PO_JSD:
         case PO_BC: {
             const int want_sum = (metric == PO_BC);
             if (want_sum && !d_aux) {
                 set_error("BC needs d_aux");
                 return PO_ERR_ARG;
             }
-            const float bias = (metric == PO_JSD) ? 1e-30f : 0.0f;
-            prepare_copy_kernel<T><<<grid, 256, 0, stream>>>(d_X, n, dim, ldx, (float*)d_P, ldp, d_aux, want_sum, bias);
+            prepare_copy_kernel<T><<<grid, 256, 0, stream>>>(d_X, n, dim, ldx, (float*)d_P, ldp, d_aux, want_sum, 0.0f);
             count_launch(2);
             PO_LAUNCH_CHECK("prepare_copy_kernel");
             return PO_OK;

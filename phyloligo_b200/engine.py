@@ -150,7 +150,8 @@ def profile_sequences(seqs, pattern, strand="both", want=("freq64",)):
 # ----------------------------------------------------------------------------
 def prepare(X, metric):
     """po_prepare_profiles: X is a device tensor (n, dim) float32/float64.
-    Returns (P int32 tensor (n, row_elems), aux float64 tensor (n,), dim)."""
+    Returns (P int32 tensor (n, words) holding po_prepared_bytes of operands,
+    aux float64 tensor (n,), dim)."""
     device = require_cuda()
     lib = _lib.load()
     if metric not in METRICS:
@@ -161,9 +162,13 @@ def prepare(X, metric):
         X = X.to(torch.float64)
     X = X.contiguous()
     n, dim = int(X.shape[0]), int(X.shape[1])
-    row_bytes = lib.po_prepared_row_bytes(METRICS[metric], dim)
-    _lib.check(row_bytes, "po_prepared_row_bytes")
-    P = torch.empty((n, row_bytes // 4), dtype=torch.int32, device=device)
+    total = lib.po_prepared_bytes(METRICS[metric], n, dim)
+    _lib.check(total, "po_prepared_bytes")
+    # a 2-D view with one row per profile keeps n visible to the callers; the buffer
+    # itself is the opaque operand layout of the library (JSD pads it to 64-profile groups)
+    words = total // 4
+    per_row = -(-words // max(1, n))
+    P = torch.empty((max(1, n) * per_row,), dtype=torch.int32, device=device)[: n * per_row].view(n, per_row)
     aux = torch.zeros((n,), dtype=torch.float64, device=device)
     rc = lib.po_prepare_profiles(METRICS[metric], _ptr(X), PO_F32 if X.dtype == torch.float32 else PO_F64,
                                  n, dim, dim, _ptr(P), _ptr(aux), _stream())
