@@ -54,7 +54,7 @@ def build_library(force=False, verbose=False, extra_flags=()):
         if (not force and os.path.isfile(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
                 and os.path.getmtime(obj) > hdr_time):
             continue
-        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-c", "-o", obj, src]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + os.environ.get("PO_NVCC_EXTRA", "").split() + ["-c", "-o", obj, src]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         jobs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -19,7 +19,6 @@ namespace po {
 constexpr int TILE = PO_TILE;   // 64
 constexpr int DK = 32;          // K elements per pipeline stage
 constexpr int PITCH = DK + 4;   // smem row pitch in words
-constexpr int NTHREADS = 256;
 
 enum Kind { K_EUCL = 0, K_KT = 2, K_BC = 3, K_SC = 4 };
 
