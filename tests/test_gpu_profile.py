@@ -88,3 +88,67 @@ def test_property_total_is_checksum_at_scale():
     digits = [(idx >> (2 * j)) & 3 for j in range(k)]  # least significant first
     rc = sum(((digits[j] ^ 1) << (2 * (k - 1 - j))) for j in range(k))
     assert torch.equal(outs["minus"]["counts"], outs["plus"]["counts"][:, torch.from_numpy(rc).cuda()])
+
+
+def _layout(seqs, rng, widths, crlf=False, blank_lines=False, trailing_space=False):
+    """FASTA text whose sequence lines have the given widths (cycled / random)."""
+    parts = []
+    for i, s in enumerate(seqs):
+        parts.append(b">r%d some description\n" % i)
+        p = 0
+        while p < len(s):
+            w = int(widths[int(rng.integers(0, len(widths)))])
+            line = s[p:p + w]
+            p += w
+            if trailing_space and rng.random() < 0.2:
+                line += b" "
+            parts.append(line + (b"\r\n" if crlf else b"\n"))
+            if blank_lines and rng.random() < 0.1:
+                parts.append(b"\n")
+    return b"".join(parts)
+
+
+def _adversarial_sequences(rng):
+    seqs = synth.make_sequences(12, 4000, seed=77)
+    seqs += [b"", b"A", b"ACG", b"ACGTACGTACGTACG", b"ACGTACGTACGTACGT", b"ACGTACGTACGTACGTA", b"N" * 300,
+             b"ACGT" * 20 + b"N" + b"TTGCA" * 30, b"acgtnACGT" * 40, b"ACGT" * 500]
+    # N runs placed around multiples of common line widths
+    s = bytearray(synth.make_sequences(1, 3000, seed=78)[0])
+    for p in (59, 60, 61, 79, 80, 81, 160, 1023, 1024, 1100):
+        s[p:p + int(rng.integers(1, 20))] = b"N" * 19
+    seqs.append(bytes(s[:3000]))
+    return seqs
+
+
+@pytest.mark.parametrize("kernel", ["auto", "general"])
+@pytest.mark.parametrize("pattern,strand", [("1111", "both"), ("1111", "minus"), ("11111", "plus"),
+                                            ("111010011", "plus"), ("1101011", "both"), ("1" * 6, "both"),
+                                            ("1001", "both"), ("10101", "minus")])
+def test_irregular_fasta_layouts(kernel, pattern, strand, monkeypatch):
+    """Line-segment fast path against the oracle on layouts that break its assumptions:
+    random line widths, widths below/at/above the segment limits, CRLF, blank lines,
+    trailing blanks, N runs across line ends."""
+    if kernel == "general":
+        monkeypatch.setenv("PO_PROFILE_KERNEL", "general")
+    else:
+        monkeypatch.delenv("PO_PROFILE_KERNEL", raising=False)
+    rng = np.random.default_rng(5)
+    seqs = _adversarial_sequences(rng)
+    expect = [po.count_vector_np(s, pattern, strand) for s in seqs]
+    layouts = [([80], False, False, False), ([60], True, False, False), ([16], False, False, False),
+               ([17], False, False, False), ([15], False, True, False), ([127], False, False, False),
+               ([128], False, False, False), ([129], False, False, True), ([500], False, False, False),
+               ([1, 2, 3, 5, 80, 81, 200], True, True, True), ([61], False, True, True), ([4], False, False, False)]
+    for widths, crlf, blank, trail in layouts:
+        text = _layout(seqs, rng, widths, crlf, blank, trail)
+        begin, end = engine.fasta_index(text)
+        assert len(begin) == len(seqs)
+        res = engine.profile_text(text, pattern, strand, want=("counts", "totals", "freq64"), begin=begin, end=end)
+        counts = res["counts"].cpu().numpy()
+        totals = res["totals"].cpu().numpy()
+        for r, (c, t) in enumerate(expect):
+            assert int(totals[r]) == t, (widths, crlf, blank, trail, r)
+            assert np.array_equal(counts[r].astype(np.int64), c), (widths, crlf, blank, trail, r)
+        f = res["freq64"].cpu().numpy()
+        for r in (0, 5, len(seqs) - 1):
+            assert np.array_equal(f[r], po.frequency_np(seqs[r], pattern, strand))
