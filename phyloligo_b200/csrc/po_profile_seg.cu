@@ -39,8 +39,16 @@ namespace po {
 
 constexpr int SEG_THREADS = 128;
 constexpr int SEG_WARPS = 4;
-constexpr int SEG_MAX_S = 128;                       // longest segment in bytes
-constexpr int SEG_STAGE_BYTES = 32 * SEG_MAX_S + 64;  // one tile (+ alignment slack)
+constexpr int SEG_MAX_S = 128;          // longest line (segment unit) in bytes
+#ifndef PO_SEG_LANE_BYTES
+#define PO_SEG_LANE_BYTES 168
+#endif
+#ifndef PO_SEG_NSTAGE
+#define PO_SEG_NSTAGE 1
+#endif
+constexpr int SEG_LANE_BYTES = PO_SEG_LANE_BYTES;      // most bytes one lane streams per tile (whole lines)
+constexpr int SEG_NSTAGE = PO_SEG_NSTAGE;              // staging buffers per warp
+constexpr int SEG_STAGE_BYTES = 32 * SEG_LANE_BYTES + 64;  // one tile (+ alignment slack)
 
 struct SegGeom {
     int width, k, nruns;
@@ -84,15 +92,12 @@ __device__ __forceinline__ uint32_t seg_classify(uint32_t c) {
     return 4u;
 }
 
-// internal bin (first base lowest digit, A C T G) -> reference bin (first base highest digit, C G A T)
+// reference bin (first base highest digit, codes C0 G1 A2 T3) -> internal bin (first base lowest
+// digit, codes A0 C1 T2 G3).  Per digit (r1 r0) -> (i1 i0) = (r0, ~r1); a full bit reversal reverses
+// the digit order and swaps the two bits of every digit, so only the inversion is left.
 __device__ __forceinline__ uint32_t seg_ref_to_internal(uint32_t r, int k) {
-    uint32_t b = 0;
-    for (int j = 0; j < k; ++j) {
-        const uint32_t rc = (r >> (2 * (k - 1 - j))) & 3u;  // reference code of base j: C0 G1 A2 T3
-        const uint32_t ic = (0x8Du >> (2 * rc)) & 3u;        // -> internal A0 C1 T2 G3: C->1, G->3, A->0, T->2
-        b |= ic << (2 * j);
-    }
-    return b;
+    const uint32_t m = (k >= 16) ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+    return ((__brev(r) >> (32 - 2 * k)) ^ 0x55555555u) & m;
 }
 // bin of the reverse-complement word, internal order (complement = code ^ 2)
 __device__ __forceinline__ uint32_t seg_revcomp_bin(uint32_t w, int k) {
@@ -190,28 +195,30 @@ profile_seg_kernel(const uint8_t* __restrict__ text, const int64_t* __restrict__
     uint32_t lastW = 0, last_inv = 0xFFFFFFFFu;
     if (end > begin) {
         const int S = (first_nl + 1 >= 17 && first_nl + 1 <= SEG_MAX_S) ? first_nl + 1 : SEG_MAX_S;
-        const int64_t nseg = (end - begin + S - 1) / S;
+        // a lane streams through L consecutive lines per tile; L balances the lanes over the fewest tiles
+        const int64_t nlines = (end - begin + S - 1) / S;
+        const int Lmax = SEG_LANE_BYTES / S;
+        const int64_t tiles_min = (nlines + 32 * Lmax - 1) / (32 * Lmax);
+        const int L = (int)((nlines + 32 * tiles_min - 1) / (32 * tiles_min));
+        const int LS = L * S;                       // bytes per lane per tile
+        const int64_t nseg = (nlines + L - 1) / L;  // lane segments in the record
         const int64_t ntiles = (nseg + 31) / 32;
         const int64_t t_lo = WARP_REC ? 0 : warp * ntiles / SEG_WARPS;
         const int64_t t_hi = WARP_REC ? ntiles : (warp + 1) * ntiles / SEG_WARPS;
-        unsigned char* wstage = stage_base + (size_t)warp * 2 * SEG_STAGE_BYTES;
+        unsigned char* wstage = stage_base + (size_t)warp * SEG_NSTAGE * SEG_STAGE_BYTES;
         const unsigned bar0 = sg_smem_u32(&s_bars[warp * 2]);
 
-        auto tile_range = [&](int64_t t, int64_t& tb, int64_t& te, int64_t& tb_al, unsigned& bytes) {
-            tb = begin + t * 32 * S;
-            te = min(end, tb + (int64_t)32 * S);
-            tb_al = tb & ~(int64_t)15;
-            bytes = (unsigned)(((te + 15) & ~(int64_t)15) - tb_al);
-        };
-        auto issue = [&](int64_t t, int it) {
-            int64_t tb, te, tb_al;
-            unsigned bytes;
-            tile_range(t, tb, te, tb_al, bytes);
-            const unsigned bar = bar0 + 8 * (it & 1);
+        const int64_t tile_stride = (int64_t)32 * LS;
+        auto issue = [&](int64_t tb, int it) {  // stage the tile that starts at byte tb
+            const int64_t te = min(end, tb + tile_stride);
+            const int64_t tb_al = tb & ~(int64_t)15;
+            const unsigned bytes = (unsigned)(((te + 15) & ~(int64_t)15) - tb_al);
+            const unsigned bar = bar0 + 8 * (it % SEG_NSTAGE);
             sg_mbar_expect_tx(bar, bytes);
-            sg_bulk_g2s(sg_smem_u32(wstage + (size_t)(it & 1) * SEG_STAGE_BYTES), text + tb_al, bytes, bar);
+            sg_bulk_g2s(sg_smem_u32(wstage + (size_t)(it % SEG_NSTAGE) * SEG_STAGE_BYTES), text + tb_al, bytes, bar);
         };
-        if (lane == 0 && t_lo < t_hi) issue(t_lo, 0);
+        int64_t tb = begin + t_lo * tile_stride;
+        if (lane == 0 && t_lo < t_hi) issue(tb, 0);
 
         // per-window shifts of the funnel {rolling register, new byte}: window ending at the
         // j-th base of a new word starts at bit 2 (17 + j - P) of that 40-bit value
@@ -223,80 +230,90 @@ profile_seg_kernel(const uint8_t* __restrict__ text, const int64_t* __restrict__
         uint32_t carryW = 0, carry_inv = 0xFFFFFFFFu;
         const int last_lane = (int)((nseg - 1) & 31);
         int it = 0;
-        for (int64_t t = t_lo; t < t_hi; ++t, ++it) {
-            if (lane == 0 && t + 1 < t_hi) issue(t + 1, it + 1);
-            int64_t tb, te, tb_al;
-            unsigned tile_bytes;
-            tile_range(t, tb, te, tb_al, tile_bytes);
-            sg_mbar_wait(bar0 + 8 * (it & 1), (unsigned)((it >> 1) & 1));
-            const unsigned char* buf = wstage + (size_t)(it & 1) * SEG_STAGE_BYTES;
+        for (int64_t t = t_lo; t < t_hi; ++t, ++it, tb += tile_stride) {
+            if (SEG_NSTAGE > 1 && lane == 0 && t + 1 < t_hi) issue(tb + tile_stride, it + 1);
+            const int64_t te = min(end, tb + tile_stride);
+            const int64_t tb_al = tb & ~(int64_t)15;
+            sg_mbar_wait(bar0 + 8 * (it % SEG_NSTAGE), (unsigned)((it / SEG_NSTAGE) & 1));
+            const unsigned char* buf = wstage + (size_t)(it % SEG_NSTAGE) * SEG_STAGE_BYTES;
 
-            const int64_t s0 = tb + (int64_t)lane * S;
-            const int64_t s1 = min(te, s0 + S);
-            const bool active = s0 < te;
+            // byte offsets inside the staged tile
+            const unsigned toff = (unsigned)(tb - tb_al);
+            const unsigned tend = (unsigned)(te - tb_al);
+            const unsigned seg0 = toff + (unsigned)lane * (unsigned)LS;
+            const bool active = seg0 < tend;
             uint32_t W = 0, inv = 0xFFFFFFFFu, headW = 0;
             bool head_ok = false;
             if (active) {
-                const unsigned off = (unsigned)(s0 - tb_al);
-                const uint32_t* wp = reinterpret_cast<const uint32_t*>(buf + (off & ~3u));
-                const unsigned sel = 0x3210u + 0x1111u * (off & 3u);
-                const unsigned char* bp = buf + off;
-                const int nbytes = (int)(s1 - s0);
-                const int nwords = nbytes >> 2;
-                uint32_t lo = wp[0];
-                int wi = 0;
-                for (; wi + 4 <= nwords; wi += 4) {
-                    uint32_t w[4], prod[4], bad = 0u;
+                const unsigned seg1 = min(tend, seg0 + (unsigned)LS);
+                for (unsigned off = seg0; off < seg1; off += (unsigned)S) {  // one line
+                    const bool first = off == seg0;
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(buf + (off & ~3u));
+                    const unsigned sel = 0x3210u + 0x1111u * (off & 3u);
+                    const unsigned char* bp = buf + off;
+                    const int nbytes = (int)(min(seg1, off + (unsigned)S) - off);
+                    const int nwords = nbytes >> 2;
+                    uint32_t lo = wp[0];
+                    uint32_t hiw[4];  // the next four aligned words, loaded one group ahead
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t hi = wp[wi + i + 1];
-                        w[i] = __byte_perm(lo, hi, sel);
-                        lo = hi;
-                        const uint32_t y = w[i] & 0x06060606u;
-                        prod[i] = y * 0x00820820u;
-                        const uint32_t tb0 = (w[i] >> 2) & ~(w[i] >> 1) & 0x01010101u;  // 1 where the code is T
-                        const uint32_t t11 = tb0 * 0x11u;
-                        bad |= ((0x41414141u | y) ^ w[i] ^ t11) & 0xDFDFDFDFu;
-                    }
-                    if (bad == 0u && wi == 0) {
-                        // first group of the segment: windows that need bases before s0 are left to
-                        // the boundary pass
+                    for (int i = 0; i < 4; ++i) hiw[i] = wp[i + 1];
+                    int wi = 0;
+                    for (; wi + 4 <= nwords; wi += 4) {
+                        uint32_t w[4], prod[4], bad = 0u;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const uint32_t nb = prod[i] >> 24;
+                            const uint32_t hi = hiw[i];
+                            hiw[i] = wp[wi + i + 5];  // may run past the line: stays inside the stage buffer
+                            w[i] = __byte_perm(lo, hi, sel);
+                            lo = hi;
+                            const uint32_t y = w[i] & 0x06060606u;
+                            prod[i] = y * 0x00820820u;
+                            const uint32_t tb0 = (w[i] >> 2) & ~(w[i] >> 1) & 0x01010101u;  // 1 where the code is T
+                            const uint32_t t11 = tb0 * 0x11u;
+                            bad |= ((0x41414141u | y) ^ w[i] ^ t11) & 0xDFDFDFDFu;
+                        }
+                        if (bad == 0u && (inv & tailmask) == 0u) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                if (4 * i + j >= P - 1) {
+                            for (int i = 0; i < 4; ++i) {
+                                const uint32_t nb = prod[i] >> 24;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
                                     const uint32_t e = __funnelshift_rc(W, nb, sh[j]);
                                     if (NRUNS == 1) bump(e & mask4);
                                     else count_window(e);
                                 }
+                                W = __byte_perm(W, prod[i], 0x7321);
                             }
-                            W = __byte_perm(W, prod[i], 0x7321);
-                        }
-                        inv = 0xFFFF0000u;
-                        headW = W;
-                        head_ok = true;
-                    } else if (bad == 0u && (inv & tailmask) == 0u) {
+                            inv <<= 16;
+                        } else if (bad == 0u && first && wi == 0) {
+                            // first group of the lane's segment: windows that need bases before it
+                            // are left to the boundary pass
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint32_t nb = prod[i] >> 24;
+                            for (int i = 0; i < 4; ++i) {
+                                const uint32_t nb = prod[i] >> 24;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint32_t e = __funnelshift_rc(W, nb, sh[j]);
-                                if (NRUNS == 1) bump(e & mask4);
-                                else count_window(e);
+                                for (int j = 0; j < 4; ++j) {
+                                    if (4 * i + j >= P - 1) {
+                                        const uint32_t e = __funnelshift_rc(W, nb, sh[j]);
+                                        if (NRUNS == 1) bump(e & mask4);
+                                        else count_window(e);
+                                    }
+                                }
+                                W = __byte_perm(W, prod[i], 0x7321);
                             }
-                            W = __byte_perm(W, prod[i], 0x7321);
+                            inv = 0xFFFF0000u;
+                            headW = W;
+                            head_ok = true;
+                        } else {
+                            for (int q = 0; q < 16; ++q) push_byte(W, inv, bp[4 * wi + q], true);
                         }
-                        inv <<= 16;
-                    } else {
-                        for (int q = 0; q < 16; ++q) push_byte(W, inv, bp[4 * wi + q], true);
                     }
+                    // what is left of the line: in a wrapped FASTA file exactly its newline
+                    if (!(nbytes - 4 * wi == 1 && bp[4 * wi] == 10u))
+                        for (int q = 4 * wi; q < nbytes; ++q) push_byte(W, inv, bp[q], true);
                 }
-                for (int q = 4 * wi; q < nbytes; ++q) push_byte(W, inv, bp[q], true);
             }
-            // ---- windows that straddle the start of this segment ----
+            // ---- windows that straddle the start of this lane's segment ----
             uint32_t prevW = __shfl_up_sync(0xFFFFFFFFu, W, 1);
             uint32_t prev_inv = __shfl_up_sync(0xFFFFFFFFu, inv, 1);
             bool have_prev = lane > 0;
@@ -311,12 +328,14 @@ profile_seg_kernel(const uint8_t* __restrict__ text, const int64_t* __restrict__
                 lastW = __shfl_sync(0xFFFFFFFFu, W, last_lane);
                 last_inv = __shfl_sync(0xFFFFFFFFu, inv, last_lane);
             }
+            const int64_t s0 = tb_al + seg0;
             if (active && P > 1 && s0 > begin) {
                 if (have_prev && head_ok && (prev_inv & tailmask) == 0u) {
                     for (int j = 0; j < P - 1; ++j) count_window(__funnelshift_r(prevW, headW, 2 * (17 + j - P)));
                 } else {
                     // generic: rebuild the P-1 bases before s0 from memory, then replay this
                     // segment's first P-1 bases
+                    const int64_t s1 = min(te, s0 + LS);
                     int need = P - 1;
                     int64_t q = s0;
                     while (q > begin && need > 0) {
@@ -336,6 +355,7 @@ profile_seg_kernel(const uint8_t* __restrict__ text, const int64_t* __restrict__
                 }
             }
             __syncwarp();  // every lane is done with this stage before it is refilled
+            if (SEG_NSTAGE == 1 && lane == 0 && t + 1 < t_hi) issue(tb + tile_stride, it + 1);
         }
     }
     rec_sync();
@@ -452,7 +472,7 @@ int launch_profile_seg(const uint8_t* d_text, const int64_t* d_begin, const int6
     const int ncopy = warp_rec ? 1 : 1;
     const int nhist = warp_rec ? SEG_WARPS : ncopy;
     const size_t hist_bytes = ((size_t)dim * nhist * 4 + 127) & ~(size_t)127;
-    const size_t smem = hist_bytes + (size_t)SEG_WARPS * 2 * SEG_STAGE_BYTES;
+    const size_t smem = hist_bytes + (size_t)SEG_WARPS * SEG_NSTAGE * SEG_STAGE_BYTES;
     const unsigned grid = warp_rec ? (unsigned)((n + SEG_WARPS - 1) / SEG_WARPS) : (unsigned)n;
     LaunchTimer t(0, stream);
 #define PO_SEG_LAUNCH(NR, WR)                                                                                        \
