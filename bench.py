@@ -14,7 +14,9 @@ already resident in HBM and the matrix left in HBM.  `e2e`: the same pass from
 pinned HOST memory (FASTA bytes -> host index -> H2D -> kernels -> every row
 panel copied back D2H into pinned buffers), all inside the timed region.
 Multi-GPU (torchrun): records are sharded for profiling, profiles all-gathered
-over NCCL, row panels of the matrix assigned cyclically to ranks.
+over NCCL; the matrix is split in contiguous block rows with balanced
+upper-triangle area, every rank computes only what lies right of the diagonal
+and sends the transposed off-diagonal blocks to the owners of those rows.
 """
 from __future__ import annotations
 
@@ -231,6 +233,7 @@ def run_ours(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=device)
     _lib.load()
 
@@ -238,12 +241,11 @@ def run_ours(args):
     fasta, total_bases = synth.fast_fasta_bytes(n_contigs, args.mean_len, seed=2)
     pairs_unique = n_contigs * (n_contigs + 1) // 2
 
-    # ---- sharding: contiguous record ranges balanced by bytes; cyclic row panels ----
+    # ---- sharding: contiguous record ranges balanced by bytes; triangle-balanced block rows ----
+    from phyloligo_b200 import sharding
     begin_all, end_all = engine.fasta_index(fasta)
     assert begin_all.shape[0] == n_contigs
-    cum = np.cumsum(end_all - begin_all)
-    cuts = [int(np.searchsorted(cum, cum[-1] * r / world)) for r in range(world)] + [n_contigs]
-    cuts[0] = 0
+    cuts = sharding.record_cuts(end_all - begin_all, world)
     rec_lo, rec_hi = cuts[rank], cuts[rank + 1]
     n_local = rec_hi - rec_lo
     n_max = max(cuts[r + 1] - cuts[r] for r in range(world))
@@ -253,9 +255,10 @@ def run_ours(args):
     pinned_text = torch.from_numpy(fasta[byte_lo:byte_hi].copy()).pin_memory()
     shard_bytes = byte_hi - byte_lo
     panel = max(64, (args.panel_rows // 64) * 64)
-    n_panels = (n_contigs + panel - 1) // panel
-    my_panels = [p for p in range(n_panels) if p % world == rank]
     symmetric = world == 1
+    bounds = sharding.triangle_row_ranges(n_contigs, world)
+    row_a, row_b = bounds[rank], bounds[rank + 1]
+    rows_owned = row_b - row_a
 
     # persistent device buffers
     d_text = torch.empty(shard_bytes + 64, dtype=torch.uint8, device=device)
@@ -267,9 +270,10 @@ def run_ours(args):
     gathered = torch.empty((world * n_max, DIM), dtype=torch.float32, device=device) if world > 1 else None
     if symmetric:
         matrix = torch.empty((n_contigs, n_contigs), dtype=torch.float32, device=device)
+        mirror_buf = None
     else:
-        rows_owned = sum(min(n_contigs, (p + 1) * panel) - p * panel for p in my_panels)
         matrix = torch.empty((max(1, rows_owned), n_contigs), dtype=torch.float32, device=device)
+        mirror_buf = torch.empty((max(1, n_contigs - row_b), max(1, rows_owned)), dtype=torch.float32, device=device)
     pin_ring = [torch.empty((panel, n_contigs), dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     pin_begin = torch.from_numpy(np.zeros(max(1, n_local), dtype=np.int64)).pin_memory()
@@ -286,43 +290,63 @@ def run_ours(args):
         parts = [gathered[r * n_max: r * n_max + (cuts[r + 1] - cuts[r])] for r in range(world)]
         return torch.cat(parts, dim=0)
 
-    def distance_panels(X, d2h):
-        """this rank's row panels; with d2h every finished panel is copied to pinned host memory"""
-        P, aux, dim = engine.prepare(X, "JSD")
-        d2h_bytes = 0
+    def d2h_panels(src_rows, n_rows):
+        """copy finished rows to the pinned ring, panel by panel (discard sink)"""
         events = [None, None]
+        d2h_bytes = 0
+        for k, r0 in enumerate(range(0, n_rows, panel)):
+            m = min(panel, n_rows - r0)
+            slot = k & 1
+            if events[slot] is not None:
+                events[slot].synchronize()  # the host consumer is done with this slot
+            pin_ring[slot][:m].copy_(src_rows[r0:r0 + m], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            events[slot] = ev
+            d2h_bytes += m * n_contigs * 4
+        return d2h_bytes
+
+    def distance_panels(X, d2h):
+        """this rank's share of the matrix; with d2h every finished row panel goes to pinned host memory"""
+        P, aux, dim = engine.prepare(X, "JSD")
         if symmetric and not d2h:
             engine.distance_block("JSD", P, aux, dim, 0, n_contigs, 0, n_contigs, matrix, 0, 0,
                                   FLAG_SKIP_LOWER | FLAG_MIRROR)
             return 0
-        row_cursor = 0
-        for k, p in enumerate(my_panels):
-            r0, r1 = p * panel, min(n_contigs, (p + 1) * panel)
-            m = r1 - r0
-            if symmetric:
+        if symmetric:
+            # panel p is complete once computed (earlier panels mirrored its left part): copy it out
+            # on the copy stream while panel p+1 computes
+            d2h_bytes = 0
+            events = [None, None]
+            for k, r0 in enumerate(range(0, n_contigs, panel)):
+                r1 = min(n_contigs, r0 + panel)
+                m = r1 - r0
                 engine.distance_block("JSD", P, aux, dim, r0, r1, 0, n_contigs, matrix, 0, 0,
                                       FLAG_SKIP_LOWER | FLAG_MIRROR)
-                src = matrix[r0:r1]
-            else:
-                src = matrix[row_cursor:row_cursor + m]
-                engine.distance_block("JSD", P, aux, dim, r0, r1, 0, n_contigs, src, r0, 0, 0)
-                row_cursor += m
-            if d2h:
                 ready = torch.cuda.Event()
                 ready.record()
                 slot = k & 1
                 if events[slot] is not None:
-                    events[slot].synchronize()  # the host consumer is done with this slot (discard sink)
+                    events[slot].synchronize()
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(ready)
-                    pin_ring[slot][:m].copy_(src, non_blocking=True)
+                    pin_ring[slot][:m].copy_(matrix[r0:r1], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(copy_stream)
                     events[slot] = ev
                 d2h_bytes += m * n_contigs * 4
-        if d2h:
             torch.cuda.current_stream().wait_stream(copy_stream)
-        return d2h_bytes
+            return d2h_bytes
+        # multi-GPU: diagonal block (mirrored in place), then everything right of it with the
+        # transposed tiles going to the exchange buffer; then the one exchange step
+        if rows_owned:
+            engine.distance_block("JSD", P, aux, dim, row_a, row_b, row_a, row_b, matrix, row_a, 0,
+                                  FLAG_SKIP_LOWER | FLAG_MIRROR)
+            if row_b < n_contigs:
+                engine.distance_block("JSD", P, aux, dim, row_a, row_b, row_b, n_contigs, matrix, row_a, 0,
+                                      FLAG_MIRROR, mirror=mirror_buf, mirror_row0=row_b, mirror_col0=row_a)
+        sharding.exchange_transposed(mirror_buf, bounds, rank, world, matrix[:rows_owned] if rows_owned else matrix[:0])
+        return d2h_panels(matrix, rows_owned) if d2h else 0
 
     def step_resident():
         X = profile_and_gather(d_begin, d_end)
@@ -397,7 +421,7 @@ def run_ours(args):
             for t0_ in range(0, n_contigs, 64):
                 pairs_per_step_computed += (min(n_contigs, t0_ + 64) - t0_) * (n_contigs - t0_)
         else:
-            pairs_per_step_computed = sum((min(n_contigs, (p + 1) * panel) - p * panel) * n_contigs for p in my_panels)
+            pairs_per_step_computed = sharding.upper_area(bounds, rank, n_contigs)
         launches_per_step = max(1, dist_n // max(1, args.steps))
         avg_launch_ms = dist_ms / max(1, dist_n)
         flop_per_launch = JSD_FLOPS_PER_PAIR * pairs_per_step_computed / launches_per_step
@@ -421,7 +445,8 @@ def run_ours(args):
                 "total_bases": total_bases, "unique_pairs": pairs_unique,
                 "pairs_computed_per_step_rank0": pairs_per_step_computed,
                 "parallelism": "1 GPU, upper triangle + mirror" if world == 1 else
-                               "%d ranks: records sharded, NCCL all-gather of profiles, cyclic row panels (full rows)" % world,
+                               "%d ranks: records sharded, NCCL all-gather of profiles, triangle-balanced block rows, "
+                               "transposed off-diagonal blocks exchanged over NCCL send/recv" % world,
                 "l2": "inputs (%.2f GB text) and outputs (%.1f GB matrix) exceed the 126 MB L2; no flush needed"
                       % (len(fasta) / 1e9, n_contigs * n_contigs * 4 / 1e9),
                 "e2e_sink": "row panels of %d rows copied D2H into a 2-slot pinned ring (discard sink)" % panel,

@@ -161,6 +161,20 @@ int po_distance_block(int metric, const void* d_P, const double* d_aux, int64_t 
                       void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0,
                       int out_dtype, unsigned flags, po_stream_t stream);
 
+/*
+ * The same block with the mirrored tiles written to a second buffer instead of `d_out`:
+ *   mirror[(c - mirror_row0) * ld_mirror + (r - mirror_col0)] = metric(profile r, profile c)
+ * for every tile that PO_FLAG_MIRROR mirrors.  This is the multi-GPU form of the
+ * reference's block-row split (gen_even_slices over rows, bin/phyloligo.py:424,516): a
+ * rank computes only the part of its block row that lies right of the diagonal and
+ * hands the transposed blocks to the ranks that own those columns as rows.
+ */
+int po_distance_block_ex(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim,
+                         int64_t row0, int64_t row1, int64_t col0, int64_t col1,
+                         void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0,
+                         void* d_mirror, int64_t ld_mirror, int64_t mirror_row0, int64_t mirror_col0,
+                         int out_dtype, unsigned flags, po_stream_t stream);
+
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t po_launch_count(void);
 

@@ -22,7 +22,7 @@ TILE = 64
 # every symbol include/phyloligo_b200.h declares (tests check the library exports them all)
 EXPORTED = [
     "po_version", "po_last_error", "po_device_info", "po_pattern_info", "po_fasta_index_host",
-    "po_profile_batch", "po_prepared_row_bytes", "po_prepared_bytes", "po_prepare_profiles", "po_distance_block",
+    "po_profile_batch", "po_prepared_row_bytes", "po_prepared_bytes", "po_prepare_profiles", "po_distance_block", "po_distance_block_ex",
     "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read", "po_microbench",
 ]
 
@@ -66,6 +66,9 @@ def load():
     lib.po_prepare_profiles.restype = i32
     lib.po_distance_block.argtypes = [i32, vp, vp, i64, i64, i64, i64, i64, i64, vp, i64, i64, i64, i32, u32, vp]
     lib.po_distance_block.restype = i32
+    lib.po_distance_block_ex.argtypes = [i32, vp, vp, i64, i64, i64, i64, i64, i64, vp, i64, i64, i64,
+                                         vp, i64, i64, i64, i32, u32, vp]
+    lib.po_distance_block_ex.restype = i32
     lib.po_launch_count.restype = i64
     lib.po_timing_enable.argtypes = [i32]
     lib.po_timing_enable.restype = i32

@@ -222,9 +222,11 @@ int po_prepare_profiles(int metric, const void* d_X, int dtype, int64_t n, int64
     return launch_prepare(metric, d_X, dtype, n, dim, ldx, d_P, d_aux, (cudaStream_t)stream);
 }
 
-int po_distance_block(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim,
-                      int64_t row0, int64_t row1, int64_t col0, int64_t col1, void* d_out, int64_t ld_out,
-                      int64_t out_row0, int64_t out_col0, int out_dtype, unsigned flags, po_stream_t stream) {
+static int distance_block_checked(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim,
+                                  int64_t row0, int64_t row1, int64_t col0, int64_t col1, void* d_out,
+                                  int64_t ld_out, int64_t out_row0, int64_t out_col0, void* d_mir, int64_t ld_mir,
+                                  int64_t mir_row0, int64_t mir_col0, int out_dtype, unsigned flags,
+                                  po_stream_t stream) {
     if (metric < PO_EUCL || metric > PO_SC) {
         set_error("unknown metric %d", metric);
         return PO_ERR_ARG;
@@ -233,7 +235,7 @@ int po_distance_block(int metric, const void* d_P, const double* d_aux, int64_t 
         set_error("unknown output dtype %d", out_dtype);
         return PO_ERR_ARG;
     }
-    if (n < 1 || dim < 1 || row0 < 0 || col0 < 0 || row1 > n || col1 > n || !d_P || !d_out) {
+    if (n < 1 || dim < 1 || row0 < 0 || col0 < 0 || row1 > n || col1 > n || !d_P || !d_out || !d_mir) {
         set_error("po_distance_block: bad arguments (n=%lld rows [%lld,%lld) cols [%lld,%lld))", (long long)n,
                   (long long)row0, (long long)row1, (long long)col0, (long long)col1);
         return PO_ERR_ARG;
@@ -246,8 +248,24 @@ int po_distance_block(int metric, const void* d_P, const double* d_aux, int64_t 
         set_error("d_P must be 16-byte aligned");
         return PO_ERR_ARG;
     }
-    return launch_distance(metric, d_P, d_aux, n, dim, row0, row1, col0, col1, d_out, ld_out, out_row0,
-                           out_col0, out_dtype, flags, (cudaStream_t)stream);
+    return launch_distance(metric, d_P, d_aux, n, dim, row0, row1, col0, col1, d_out, ld_out, out_row0, out_col0,
+                           d_mir, ld_mir, mir_row0, mir_col0, out_dtype, flags, (cudaStream_t)stream);
+}
+
+int po_distance_block(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim,
+                      int64_t row0, int64_t row1, int64_t col0, int64_t col1, void* d_out, int64_t ld_out,
+                      int64_t out_row0, int64_t out_col0, int out_dtype, unsigned flags, po_stream_t stream) {
+    return distance_block_checked(metric, d_P, d_aux, n, dim, row0, row1, col0, col1, d_out, ld_out, out_row0,
+                                  out_col0, d_out, ld_out, out_row0, out_col0, out_dtype, flags, stream);
+}
+
+int po_distance_block_ex(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim,
+                         int64_t row0, int64_t row1, int64_t col0, int64_t col1, void* d_out, int64_t ld_out,
+                         int64_t out_row0, int64_t out_col0, void* d_mirror, int64_t ld_mirror,
+                         int64_t mirror_row0, int64_t mirror_col0, int out_dtype, unsigned flags,
+                         po_stream_t stream) {
+    return distance_block_checked(metric, d_P, d_aux, n, dim, row0, row1, col0, col1, d_out, ld_out, out_row0,
+                                  out_col0, d_mirror, ld_mirror, mirror_row0, mirror_col0, out_dtype, flags, stream);
 }
 
 int64_t po_launch_count(void) { return g_launches.load(); }

@@ -66,6 +66,7 @@ int launch_prepare(int metric, const void* d_X, int dtype, int64_t n, int64_t di
 int launch_distance(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim,
                     int64_t row0, int64_t row1, int64_t col0, int64_t col1,
                     void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0,
+                    void* d_mir, int64_t ld_mir, int64_t mir_row0, int64_t mir_col0,
                     int out_dtype, unsigned flags, cudaStream_t stream);
 
 // number of 32-bit elements of one prepared row (JSD: of one operand copy)
@@ -74,7 +75,7 @@ int64_t prepared_row_elems(int metric, int64_t dim);
 int64_t prepared_bytes(int metric, int64_t n, int64_t dim);
 
 int launch_jsd(const void* d_P, int64_t n, int64_t dim, int64_t row0, int64_t row1, int64_t col0, int64_t col1,
-               void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0, int out_dtype, unsigned flags,
-               cudaStream_t stream);
+               void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0, void* d_mir, int64_t ld_mir,
+               int64_t mir_row0, int64_t mir_col0, int out_dtype, unsigned flags, cudaStream_t stream);
 
 }  // namespace po

@@ -132,6 +132,8 @@ struct TileParams {
     int64_t row0, row1, col0, col1;
     void* out;
     int64_t ld_out, out_row0, out_col0;
+    void* mir;            // where mirrored tiles go (== out unless the caller gave a separate buffer)
+    int64_t ld_mir, mir_row0, mir_col0;
     unsigned flags;
     int kdim;             // number of elements to stream (== ldp)
 };
@@ -266,10 +268,11 @@ __global__ void __launch_bounds__(4 * TM, 2) distance_tile_kernel(const TilePara
             out[(row_base + r - p.out_row0) * p.ld_out + (col_base + c - p.out_col0)] = tile[r * TP + c];
     }
     if ((p.flags & PO_FLAG_MIRROR) && row_base + TM <= col_base) {
+        OUT_T* mir = reinterpret_cast<OUT_T*>(p.mir);
         for (int e = tid; e < TM * TN; e += NT) {
             const int c = e / TM, r = e % TM;  // consecutive threads walk r: contiguous in the mirrored row
             if (r < rmax && c < cmax)
-                out[(col_base + c - p.out_row0) * p.ld_out + (row_base + r - p.out_col0)] = tile[r * TP + c];
+                mir[(col_base + c - p.mir_row0) * p.ld_mir + (row_base + r - p.mir_col0)] = tile[r * TP + c];
         }
     }
 }
@@ -295,6 +298,7 @@ static int launch_kind(const TileParams& p, int out_dtype, cudaStream_t stream) 
 int launch_distance(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim,
                     int64_t row0, int64_t row1, int64_t col0, int64_t col1,
                     void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0,
+                    void* d_mir, int64_t ld_mir, int64_t mir_row0, int64_t mir_col0,
                     int out_dtype, unsigned flags, cudaStream_t stream) {
     if (row1 <= row0 || col1 <= col0) return PO_OK;
     TileParams p;
@@ -305,12 +309,13 @@ int launch_distance(int metric, const void* d_P, const double* d_aux, int64_t n,
     p.n = n;
     p.row0 = row0; p.row1 = row1; p.col0 = col0; p.col1 = col1;
     p.out = d_out; p.ld_out = ld_out; p.out_row0 = out_row0; p.out_col0 = out_col0;
+    p.mir = d_mir; p.ld_mir = ld_mir; p.mir_row0 = mir_row0; p.mir_col0 = mir_col0;
     p.flags = flags;
     switch (metric) {
         case PO_EUCL: return launch_kind<K_EUCL, 64>(p, out_dtype, stream);
         case PO_JSD:
-            return launch_jsd(d_P, n, dim, row0, row1, col0, col1, d_out, ld_out, out_row0, out_col0, out_dtype,
-                              flags, stream);
+            return launch_jsd(d_P, n, dim, row0, row1, col0, col1, d_out, ld_out, out_row0, out_col0, d_mir, ld_mir,
+                              mir_row0, mir_col0, out_dtype, flags, stream);
         case PO_BC: return launch_kind<K_BC, 64>(p, out_dtype, stream);
         case PO_SC: return launch_kind<K_SC, 64>(p, out_dtype, stream);
         case PO_KT: return launch_kind<K_KT, 64>(p, out_dtype, stream);

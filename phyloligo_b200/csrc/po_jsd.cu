@@ -160,6 +160,8 @@ struct JsdParams {
     int64_t tile_row0, tile_col0;  // first tile origin (multiples of 32 / 64)
     void* out;
     int64_t ld_out, out_row0, out_col0;
+    void* mir;  // where mirrored tiles go (== out unless the caller gave a separate buffer)
+    int64_t ld_mir, mir_row0, mir_col0;
     unsigned flags;
 };
 
@@ -323,17 +325,18 @@ __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdP
             out[(row_base + r - p.out_row0) * p.ld_out + (col_base + c - p.out_col0)] = tile[r * TP + c];
     }
     if ((p.flags & PO_FLAG_MIRROR) && row_base + JT_M <= col_base) {
+        OUT_T* mir = reinterpret_cast<OUT_T*>(p.mir);
         for (int e = tid; e < JT_M * JT_N; e += JTHREADS) {
             const int c = e >> 5, r = e & 31;  // consecutive threads walk r: contiguous in the mirrored row
             if (r >= r_lo && r < r_hi && c >= c_lo && c < c_hi)
-                out[(col_base + c - p.out_row0) * p.ld_out + (row_base + r - p.out_col0)] = tile[r * TP + c];
+                mir[(col_base + c - p.mir_row0) * p.ld_mir + (row_base + r - p.mir_col0)] = tile[r * TP + c];
         }
     }
 }
 
 int launch_jsd(const void* d_P, int64_t n, int64_t dim, int64_t row0, int64_t row1, int64_t col0, int64_t col1,
-               void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0, int out_dtype, unsigned flags,
-               cudaStream_t stream) {
+               void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0, void* d_mir, int64_t ld_mir,
+               int64_t mir_row0, int64_t mir_col0, int out_dtype, unsigned flags, cudaStream_t stream) {
     const int64_t ldp = prepared_row_elems(PO_JSD, dim);
     const int64_t npad = (n + 63) / 64 * 64;
     JsdParams p;
@@ -345,6 +348,7 @@ int launch_jsd(const void* d_P, int64_t n, int64_t dim, int64_t row0, int64_t ro
     p.tile_row0 = row0 / JT_M * JT_M;
     p.tile_col0 = col0 / JT_N * JT_N;
     p.out = d_out; p.ld_out = ld_out; p.out_row0 = out_row0; p.out_col0 = out_col0;
+    p.mir = d_mir; p.ld_mir = ld_mir; p.mir_row0 = mir_row0; p.mir_col0 = mir_col0;
     p.flags = flags;
     const int64_t tr = (row1 - p.tile_row0 + JT_M - 1) / JT_M, tc = (col1 - p.tile_col0 + JT_N - 1) / JT_N;
     if (tr > 65535) {

@@ -176,13 +176,23 @@ def prepare(X, metric):
     return P, aux, dim
 
 
-def distance_block(metric, P, aux, dim, row0, row1, col0, col1, out, out_row0, out_col0, flags=0):
-    """po_distance_block into the device tensor `out` (2-D, float32 or float64)."""
+def distance_block(metric, P, aux, dim, row0, row1, col0, col1, out, out_row0, out_col0, flags=0,
+                   mirror=None, mirror_row0=0, mirror_col0=0):
+    """po_distance_block into the device tensor `out` (2-D, float32 or float64).  With
+    `mirror` (same dtype) the mirrored tiles go to mirror[c - mirror_row0, r - mirror_col0]."""
     lib = _lib.load()
     n = int(P.shape[0])
-    rc = lib.po_distance_block(METRICS[metric], _ptr(P), _ptr(aux), n, dim, row0, row1, col0, col1,
-                               _ptr(out), int(out.stride(0)), out_row0, out_col0,
-                               PO_F32 if out.dtype == torch.float32 else PO_F64, flags, _stream())
+    dt = PO_F32 if out.dtype == torch.float32 else PO_F64
+    if mirror is None:
+        rc = lib.po_distance_block(METRICS[metric], _ptr(P), _ptr(aux), n, dim, row0, row1, col0, col1,
+                                   _ptr(out), int(out.stride(0)), out_row0, out_col0, dt, flags, _stream())
+    else:
+        if mirror.dtype != out.dtype:
+            raise PhyloligoError("mirror buffer must have the dtype of the output")
+        rc = lib.po_distance_block_ex(METRICS[metric], _ptr(P), _ptr(aux), n, dim, row0, row1, col0, col1,
+                                      _ptr(out), int(out.stride(0)), out_row0, out_col0,
+                                      _ptr(mirror), int(mirror.stride(0)), mirror_row0, mirror_col0, dt, flags,
+                                      _stream())
     _lib.check(rc, "po_distance_block")
 
 
