@@ -108,7 +108,10 @@ int po_profile_batch(const uint8_t* d_text, const int64_t* d_begin, const int64_
 /*
  * Size in bytes of the prepared operand buffer (the layout po_distance_block consumes)
  * of n profiles of dimension `dim` for `metric`; the caller allocates it.
- *   Eucl / BC : n rows of dim rounded up to a multiple of 4, float32
+ *   Eucl      : dim >= 256: centred float16 hi/lo operand blocks for the tensor-core kernel
+ *               (n rounded up to 128, dim to 64, 4 bytes per element) + dim float64 column sums;
+ *               dim < 256 or PO_EUCL_EXACT=1: as BC
+ *   BC        : n rows of dim rounded up to a multiple of 4, float32
  *   SC        : the same count of int32 (centred doubled average ranks)
  *   KT        : n rows of packed order-relation bit masks, 2 * ceil(dim(dim-1)/2 / 128) * 16 bytes
  *   JSD       : float32 with exact zeros biased to 1e-30, dim rounded up to a multiple of 32
@@ -126,6 +129,7 @@ int64_t po_prepared_row_bytes(int metric, int64_t dim);
  *   d_X       [n x ldx] profiles, float32 or float64 (`dtype`), ldx in elements
  *   d_P       po_prepared_bytes(metric, n, dim) bytes of prepared operands (written), 16-byte aligned
  *   d_aux     [n] float64 per-row constant (written):
+ *               Eucl (tensor-core path): squared norm of the centred, scaled row
  *               SC: sum of squares of the centred doubled ranks (0 = constant row)
  *               KT: number of element pairs that are not tied in the row
  *               others: unused (may be NULL)
@@ -151,7 +155,8 @@ int po_prepare_profiles(int metric, const void* d_X, int dtype, int64_t n, int64
  *   flags        PO_FLAG_SKIP_LOWER / PO_FLAG_MIRROR exploit symmetry when the
  *                caller's `out` addresses the full matrix (mirrored entries
  *                (c, r) must be addressable).
- * Values: Eucl = sqrt(sum (a-b)^2); JSD in nats (core/phylodist.py:22), 0 for
+ * Values: Eucl = sqrt(sum (a-b)^2) (dim >= 256: Gram form on the tensor cores, exact 0 on the
+ * diagonal, stated tolerance 1e-4 relative, measured ~1e-6; PO_EUCL_EXACT=1 forces the exact kernel); JSD in nats (core/phylodist.py:22), 0 for
  * identical rows, ln(2)/2 against an all-zero row; BC = sum|a-b| / sum|a+b|;
  * KT = 1 - (1 - tau_b) (tau_b itself; 0 when a row is constant); SC = 1 - rho
  * (NaN when a row is constant).

@@ -69,6 +69,15 @@ int launch_distance(int metric, const void* d_P, const double* d_aux, int64_t n,
                     void* d_mir, int64_t ld_mir, int64_t mir_row0, int64_t mir_col0,
                     int out_dtype, unsigned flags, cudaStream_t stream);
 
+// Euclidean distances on the tensor cores (po_gram.cu)
+bool eucl_use_gram(int64_t dim);
+int64_t gram_prepared_bytes(int64_t n, int64_t dim);
+int launch_gram_prepare(const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx, void* d_P, double* d_aux,
+                        cudaStream_t stream);
+int launch_gram(const void* d_P, const double* d_aux, int64_t n, int64_t dim, int64_t row0, int64_t row1, int64_t col0,
+                int64_t col1, void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0, void* d_mir,
+                int64_t ld_mir, int64_t mir_row0, int64_t mir_col0, int out_dtype, unsigned flags, cudaStream_t stream);
+
 // number of 32-bit elements of one prepared row (JSD: of one operand copy)
 int64_t prepared_row_elems(int metric, int64_t dim);
 // total bytes of the prepared operand buffer of n rows

@@ -1,0 +1,446 @@
+// Euclidean distance tiles on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces euclidean_distances_loc / euclidean_distances_h5py -> sklearn
+// euclidean_distances (reference bin/phyloligo.py:200-202, 238-246: the Gram form
+// ||x||^2 + ||y||^2 - 2 x.y, clamped at 0, square root, exact 0 on the diagonal) and
+// phylodist.Eucl (core/phylodist.py:36-41) for profile dimensions >= 256.
+//
+// Numerics.  The Gram form cancels, so the operands are conditioned first:
+//   * centring: x' = x - mean profile (a Euclidean distance is translation invariant);
+//     ||x'|| is then of the order of the distances themselves instead of ~1/sqrt(D);
+//   * x' * 2^14 is split into two float16 values hi + lo (22 significant bits); the tensor
+//     cores form hi.hi, hi.lo and lo.hi in three separate float32 accumulators in TMEM
+//     (the dropped lo.lo term is 2^-22 relative) and the epilogue adds hh + (hl + lh): every
+//     accumulator sees the same products in the same order for (r, c) and (c, r), so the
+//     matrix is bitwise symmetric whichever tile computes an entry;
+//   * the row norms are float64 sums over the very same hi + lo values, and the epilogue
+//     evaluates n_a + n_b - 2 dot in float64.
+//   * entries whose Gram form cancels by more than 2^8 (n_a + n_b > 256 d^2: near-duplicate
+//     profiles) are recomputed exactly as sum (a-b)^2 by the warp that owns them, from a
+//     float32 copy of the profiles kept next to the operand blocks.
+// Measured error against the float64 oracle is ~1e-8 relative for ordinary pairs and below
+// 5e-5 at the cancellation threshold; the stated tolerance of this path is 1e-4
+// (BASELINE.json north_star).  PO_EUCL_EXACT=1 (or dim < 256) selects
+// the exact CUDA-core kernel of po_distance.cu instead.
+//
+// Layout.  po_prepare_profiles writes, for every group of 128 profiles and every block of
+// 64 dimensions, the hi block and the lo block (16 KB each) in the canonical no-swizzle
+// K-major UMMA shared-memory layout: 8x16-byte core matrices, 128 B apart along the rows
+// and 2 KB apart along K.  A CTA computes one 128 x 128 tile: one thread streams the four
+// blocks of a K block (A hi/lo, B hi/lo) with cp.async.bulk into a 3-stage ring, one thread
+// issues 12 tcgen05.mma (128x128x16, kind::f16) per stage and commits them to the stage's
+// "empty" barrier, and after the last commit all four warps read the accumulator with
+// tcgen05.ld (one row per thread), finish the distance and store the tile (and its mirror).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include "po_common.cuh"
+
+namespace po {
+
+constexpr int GT = 128;                 // tile edge (M = N = 128)
+constexpr int GK = 64;                  // K elements per block (4 MMAs of K = 16)
+constexpr int GBLOCK_BYTES = GT * GK * 2;     // one operand block: 16 KB
+constexpr int GSTAGE_BYTES = 4 * GBLOCK_BYTES;  // A hi, A lo, B hi, B lo
+constexpr int GSTAGES = 3;
+constexpr int GTHREADS = 128;
+constexpr float GSCALE = 16384.0f;      // 2^14
+constexpr double GUNSCALE = 1.0 / (16384.0 * 16384.0);
+
+bool eucl_use_gram(int64_t dim) {
+    const char* e = getenv("PO_EUCL_EXACT");
+    if (e && e[0] == '1') return false;
+    return dim >= 256;
+}
+int64_t gram_ldk(int64_t dim) { return (dim + GK - 1) / GK * GK; }
+constexpr int GSUM_SLICES = 256;  // row slices of the two-stage (order-fixed, reproducible) column sums
+// operand blocks, then the float64 column sums used for centring, then a float32 copy of the
+// profiles (row pitch ldk) for the exact recomputation of cancelling entries, then the
+// per-slice partial column sums
+int64_t gram_prepared_bytes(int64_t n, int64_t dim) {
+    const int64_t npad = (n + GT - 1) / GT * GT;
+    const int64_t ldk = gram_ldk(dim);
+    return npad * ldk * 4 + ldk * 8 + n * ldk * 4 + (int64_t)GSUM_SLICES * ldk * 8;
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand preparation
+// ---------------------------------------------------------------------------------------------
+// Column sums in two stages with a fixed summation order (no atomics): the result must be
+// bit-reproducible, every rank of a multi-GPU run prepares the same operands.
+template <typename T>
+__global__ void __launch_bounds__(256) gram_colsum_kernel(const T* __restrict__ X, int64_t n, int64_t dim, int64_t ldx,
+                                                          double* __restrict__ partial, int64_t ldk) {
+    const int64_t col = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (col >= dim) return;
+    const int64_t rows_per = (n + GSUM_SLICES - 1) / GSUM_SLICES;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
+    double s = 0.0;
+    for (int64_t r = r0; r < r1; ++r) s += (double)X[r * ldx + col];
+    partial[(int64_t)blockIdx.y * ldk + col] = s;
+}
+__global__ void __launch_bounds__(256) gram_colsum_final_kernel(const double* __restrict__ partial, int64_t dim,
+                                                                int64_t ldk, double* __restrict__ sums) {
+    const int64_t col = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (col >= ldk) return;
+    double s = 0.0;
+    if (col < dim)
+        for (int y = 0; y < GSUM_SLICES; ++y) s += partial[(int64_t)y * ldk + col];
+    sums[col] = s;
+}
+
+// One CTA per group of 128 profiles; the K blocks are walked in order so that a row's squared
+// norm is accumulated in a fixed order (reproducible, no atomics).
+template <typename T>
+__global__ void __launch_bounds__(256) gram_blocks_kernel(const T* __restrict__ X, int64_t n, int64_t dim, int64_t ldx,
+                                                          const double* __restrict__ sums, unsigned char* __restrict__ P,
+                                                          int nkb, double* __restrict__ aux, float* __restrict__ X32) {
+    const int64_t grp = blockIdx.x;
+    const double inv_n = 1.0 / (double)n;
+    double nrm[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int kb = 0; kb < nkb; ++kb) {
+        unsigned char* blk_hi = P + ((size_t)grp * nkb + kb) * 2 * GBLOCK_BYTES;
+        unsigned char* blk_lo = blk_hi + GBLOCK_BYTES;
+        // thread -> (row, chunk of 8 dimensions): 128 rows x 8 chunks = 1024 items, 4 per thread
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int item = threadIdx.x + 256 * it;
+            const int row = item >> 3, chunk = item & 7;
+            const int64_t r = grp * GT + row;
+            __half hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int64_t k = (int64_t)kb * GK + chunk * 8 + e;
+                float v = 0.f, x = 0.f;
+                if (r < n && k < dim) {
+                    x = (float)X[r * ldx + k];
+                    v = (x - (float)(sums[k] * inv_n)) * GSCALE;
+                }
+                if (r < n) X32[r * ((int64_t)nkb * GK) + k] = x;
+                hi[e] = __float2half_rn(v);
+                lo[e] = __float2half_rn(v - __half2float(hi[e]));
+                const double q = (double)__half2float(hi[e]) + (double)__half2float(lo[e]);
+                nrm[it] += q * q;
+            }
+            const size_t off = ((size_t)chunk * 16 + (row >> 3)) * 128 + (row & 7) * 16;
+            *reinterpret_cast<uint4*>(blk_hi + off) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(blk_lo + off) = *reinterpret_cast<const uint4*>(lo);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        // the 8 chunks of a row sit in 8 consecutive threads
+        double v = nrm[it];
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 1);
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 2);
+        v += __shfl_xor_sync(0xFFFFFFFFu, v, 4);
+        const int item = threadIdx.x + 256 * it;
+        const int64_t r = grp * GT + (item >> 3);
+        if ((item & 7) == 0 && r < n) aux[r] = v;
+    }
+}
+
+template <typename T>
+static int launch_gram_prepare_t(const void* d_X, int64_t n, int64_t dim, int64_t ldx, void* d_P, double* d_aux,
+                                 cudaStream_t stream) {
+    const int64_t ldk = gram_ldk(dim);
+    const int64_t npad = (n + GT - 1) / GT * GT;
+    const int nkb = (int)(ldk / GK);
+    unsigned char* P = reinterpret_cast<unsigned char*>(d_P);
+    double* sums = reinterpret_cast<double*>(P + npad * ldk * 4);
+    float* X32 = reinterpret_cast<float*>(P + npad * ldk * 4 + ldk * 8);
+    double* partial = reinterpret_cast<double*>(P + npad * ldk * 4 + ldk * 8 + n * ldk * 4);
+    dim3 g1((unsigned)((dim + 255) / 256), GSUM_SLICES, 1);
+    gram_colsum_kernel<T><<<g1, 256, 0, stream>>>(reinterpret_cast<const T*>(d_X), n, dim, ldx, partial, ldk);
+    count_launch(2);
+    PO_LAUNCH_CHECK("gram_colsum_kernel");
+    gram_colsum_final_kernel<<<(unsigned)((ldk + 255) / 256), 256, 0, stream>>>(partial, dim, ldk, sums);
+    count_launch(2);
+    PO_LAUNCH_CHECK("gram_colsum_final_kernel");
+    gram_blocks_kernel<T><<<(unsigned)(npad / GT), 256, 0, stream>>>(reinterpret_cast<const T*>(d_X), n, dim, ldx, sums, P,
+                                                                    nkb, d_aux, X32);
+    count_launch(2);
+    PO_LAUNCH_CHECK("gram_blocks_kernel");
+    return PO_OK;
+}
+
+int launch_gram_prepare(const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx, void* d_P, double* d_aux,
+                        cudaStream_t stream) {
+    if (!d_aux) {
+        set_error("Eucl (tensor-core path) needs d_aux");
+        return PO_ERR_ARG;
+    }
+    if (dtype == PO_F32) return launch_gram_prepare_t<float>(d_X, n, dim, ldx, d_P, d_aux, stream);
+    return launch_gram_prepare_t<double>(d_X, n, dim, ldx, d_P, d_aux, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile kernel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned g_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void g_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void g_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol error traps instead of hanging the device
+__device__ __forceinline__ void g_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void g_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// no-swizzle K-major operand descriptor: core matrices 128 B apart along M/N (SBO), 2 KB apart along K (LBO)
+__device__ __forceinline__ uint64_t g_smem_desc(unsigned saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);         // start address
+    d |= (uint64_t)((2048u >> 4) & 0x3FFFu) << 16;   // leading byte offset (K direction)
+    d |= (uint64_t)((128u >> 4) & 0x3FFFu) << 32;    // stride byte offset (M/N direction)
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    return d;                                        // layout type 0: no swizzle
+}
+__device__ __forceinline__ void g_mma_f16(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void g_mma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void g_tmem_ld16(unsigned taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void g_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct GramParams {
+    const unsigned char* P;  // operand blocks [n/128 groups][nkb][hi | lo][16 KB]
+    const float* X32;        // float32 copy of the profiles, row pitch nkb * 64
+    const double* aux;       // squared norms of the scaled, centred rows
+    int nkb;
+    int64_t n;
+    int64_t row0, row1, col0, col1;
+    int64_t tile_row0, tile_col0;
+    void* out;
+    int64_t ld_out, out_row0, out_col0;
+    void* mir;
+    int64_t ld_mir, mir_row0, mir_col0;
+    unsigned flags;
+};
+
+template <typename OUT_T>
+__global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams p) {
+    extern __shared__ __align__(1024) unsigned char gsmem[];
+    __shared__ __align__(8) unsigned long long bars[2 * GSTAGES + 1];
+    __shared__ uint32_t s_tmem;
+    const int64_t row_base = p.tile_row0 + (int64_t)blockIdx.y * GT;
+    const int64_t col_base = p.tile_col0 + (int64_t)blockIdx.x * GT;
+    if ((p.flags & PO_FLAG_SKIP_LOWER) && col_base + GT <= row_base) return;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned smem0 = g_smem_u32(gsmem);
+    const unsigned full0 = g_smem_u32(&bars[0]), empty0 = g_smem_u32(&bars[GSTAGES]), accum = g_smem_u32(&bars[2 * GSTAGES]);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < GSTAGES; ++s) {
+            g_mbar_init(full0 + 8 * s, 1);
+            g_mbar_init(empty0 + 8 * s, 1);
+        }
+        g_mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // one warp allocates the TMEM columns (three 128 x 128 float32 accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(&s_tmem)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = s_tmem;
+
+    const int nkb = p.nkb;
+    const unsigned char* gA = p.P + (size_t)(row_base / GT) * nkb * 2 * GBLOCK_BYTES;
+    const unsigned char* gB = p.P + (size_t)(col_base / GT) * nkb * 2 * GBLOCK_BYTES;
+
+    if (warp == 0 && lane == 0) {
+        // ===== producer: four bulk copies per K block =====
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % GSTAGES;
+            g_mbar_wait(empty0 + 8 * s, (unsigned)(((kb / GSTAGES) & 1) ^ 1));
+            const unsigned dst = smem0 + s * GSTAGE_BYTES;
+            g_mbar_expect_tx(full0 + 8 * s, GSTAGE_BYTES);
+            g_bulk_g2s(dst, gA + (size_t)kb * 2 * GBLOCK_BYTES, 2 * GBLOCK_BYTES, full0 + 8 * s);
+            g_bulk_g2s(dst + 2 * GBLOCK_BYTES, gB + (size_t)kb * 2 * GBLOCK_BYTES, 2 * GBLOCK_BYTES, full0 + 8 * s);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        // instruction descriptor: D float32, A/B float16 K-major, N = 128, M = 128
+        const unsigned idesc = (1u << 4) | ((unsigned)(GT >> 3) << 17) | ((unsigned)(GT >> 4) << 24);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % GSTAGES;
+            g_mbar_wait(full0 + 8 * s, (unsigned)((kb / GSTAGES) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned a_hi = smem0 + s * GSTAGE_BYTES, a_lo = a_hi + GBLOCK_BYTES;
+            const unsigned b_hi = a_hi + 2 * GBLOCK_BYTES, b_lo = b_hi + GBLOCK_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < GK / 16; ++ks) {
+                const unsigned koff = ks * 2 * 2048;  // two 8-element chunks per MMA
+                const uint64_t dah = g_smem_desc(a_hi + koff), dal = g_smem_desc(a_lo + koff);
+                const uint64_t dbh = g_smem_desc(b_hi + koff), dbl = g_smem_desc(b_lo + koff);
+                const unsigned acc = (kb > 0 || ks > 0) ? 1u : 0u;
+                g_mma_f16(tmem, dah, dbh, idesc, acc);
+                g_mma_f16(tmem + GT, dah, dbl, idesc, acc);
+                g_mma_f16(tmem + 2 * GT, dal, dbh, idesc, acc);
+            }
+            g_mma_commit(empty0 + 8 * s);  // the stage is free once these MMAs have read it
+        }
+        g_mma_commit(accum);  // accumulator complete
+    }
+    __syncwarp();
+
+    // ===== epilogue: one accumulator row per thread =====
+    g_mbar_wait(accum, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int r = warp * 32 + lane;  // tile row == TMEM lane
+    const int64_t grow = row_base + r;
+    const bool row_ok = grow >= p.row0 && grow < p.row1;
+    const double na = (grow < p.n) ? p.aux[grow] : 0.0;
+    OUT_T* out = reinterpret_cast<OUT_T*>(p.out);
+    OUT_T* mir = reinterpret_cast<OUT_T*>(p.mir);
+    const bool do_mirror = (p.flags & PO_FLAG_MIRROR) && row_base + GT <= col_base;
+    const int64_t ldx32 = (int64_t)nkb * GK;
+#pragma unroll 1
+    for (int c0 = 0; c0 < GT; c0 += 16) {
+        uint32_t vh[16], vx[16], vy[16];
+        const unsigned ta = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
+        g_tmem_ld16(ta, vh);
+        g_tmem_ld16(ta + GT, vx);
+        g_tmem_ld16(ta + 2 * GT, vy);
+        g_tmem_wait_ld();
+        OUT_T val[16];
+        unsigned cancel = 0u;  // columns of this chunk whose Gram form cancelled too much
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int64_t gcol = col_base + c0 + j;
+            const double nb = (gcol < p.n) ? p.aux[gcol] : 0.0;
+            const float dot = __uint_as_float(vh[j]) + (__uint_as_float(vx[j]) + __uint_as_float(vy[j]));
+            double d2 = na + nb - 2.0 * (double)dot;
+            const bool inside = row_ok && gcol >= p.col0 && gcol < p.col1;
+            if (inside && grow != gcol && d2 * 256.0 < na + nb) cancel |= 1u << j;
+            d2 = (d2 > 0.0 ? d2 : 0.0) * GUNSCALE;
+            if (sizeof(OUT_T) == 8) val[j] = (OUT_T)sqrt(d2);
+            else val[j] = (OUT_T)sqrtf((float)d2);
+            if (grow == gcol) val[j] = (OUT_T)0;  // sklearn forces an exact zero diagonal
+        }
+        // exact recomputation, one entry at a time, by the whole warp
+        unsigned lanes = __ballot_sync(0xFFFFFFFFu, cancel != 0u);
+        while (lanes) {
+            const int l = __ffs(lanes) - 1;
+            lanes &= lanes - 1;
+            unsigned m = __shfl_sync(0xFFFFFFFFu, cancel, l);
+            const int64_t er = row_base + warp * 32 + l;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const float* xa = p.X32 + er * ldx32;
+                const float* xb = p.X32 + (col_base + c0 + j) * ldx32;
+                double acc = 0.0;
+                for (int64_t k0 = 0; k0 < ldx32; k0 += 1024) {  // float32 partial sums of <= 32 terms per lane
+                    float part = 0.f;
+                    const int64_t k1 = min(ldx32, k0 + 1024);
+                    for (int64_t k = k0 + lane; k < k1; k += 32) {
+                        const float d = xa[k] - xb[k];
+                        part = fmaf(d, d, part);
+                    }
+                    acc += (double)part;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+                if (lane == l) {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj)
+                        if (jj == j) val[jj] = (sizeof(OUT_T) == 8) ? (OUT_T)sqrt(acc) : (OUT_T)sqrtf((float)acc);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int64_t gcol = col_base + c0 + j;
+            if (row_ok && gcol >= p.col0 && gcol < p.col1) {
+                out[(grow - p.out_row0) * p.ld_out + (gcol - p.out_col0)] = val[j];
+                if (do_mirror) mir[(gcol - p.mir_row0) * p.ld_mir + (grow - p.mir_col0)] = val[j];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}
+
+int launch_gram(const void* d_P, const double* d_aux, int64_t n, int64_t dim, int64_t row0, int64_t row1, int64_t col0,
+                int64_t col1, void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0, void* d_mir,
+                int64_t ld_mir, int64_t mir_row0, int64_t mir_col0, int out_dtype, unsigned flags, cudaStream_t stream) {
+    if (!d_aux) {
+        set_error("Eucl (tensor-core path) needs d_aux from po_prepare_profiles");
+        return PO_ERR_ARG;
+    }
+    GramParams p;
+    p.P = reinterpret_cast<const unsigned char*>(d_P);
+    p.aux = d_aux;
+    p.nkb = (int)(gram_ldk(dim) / GK);
+    {
+        const int64_t ldk = gram_ldk(dim), npad = (n + GT - 1) / GT * GT;
+        p.X32 = reinterpret_cast<const float*>(p.P + npad * ldk * 4 + ldk * 8);
+    }
+    p.n = n;
+    p.row0 = row0; p.row1 = row1; p.col0 = col0; p.col1 = col1;
+    p.tile_row0 = row0 / GT * GT;
+    p.tile_col0 = col0 / GT * GT;
+    p.out = d_out; p.ld_out = ld_out; p.out_row0 = out_row0; p.out_col0 = out_col0;
+    p.mir = d_mir; p.ld_mir = ld_mir; p.mir_row0 = mir_row0; p.mir_col0 = mir_col0;
+    p.flags = flags;
+    const int64_t tr = (row1 - p.tile_row0 + GT - 1) / GT, tc = (col1 - p.tile_col0 + GT - 1) / GT;
+    if (tr > 65535) {
+        set_error("row block too tall: %lld rows (max %d per call)", (long long)(row1 - row0), 65535 * GT);
+        return PO_ERR_UNSUPPORTED;
+    }
+    const size_t smem = (size_t)GSTAGES * GSTAGE_BYTES + 1024;
+    dim3 grid((unsigned)tc, (unsigned)tr, 1);
+    LaunchTimer tm(1, stream);
+    if (out_dtype == PO_F32) {
+        PO_CUDA_CHECK(cudaFuncSetAttribute(gram_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gram_tile_kernel<float><<<grid, GTHREADS, smem, stream>>>(p);
+    } else {
+        PO_CUDA_CHECK(cudaFuncSetAttribute(gram_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gram_tile_kernel<double><<<grid, GTHREADS, smem, stream>>>(p);
+    }
+    count_launch(1);
+    PO_LAUNCH_CHECK("gram_tile_kernel");
+    return PO_OK;
+}
+
+}  // namespace po

@@ -2,8 +2,9 @@
 the reference golden matrices and the oracle.
 
 Tolerances (BASELINE.json north_star): Eucl / BC / JSD <= 1e-6 relative against the
-float64-accumulated oracle on the same inputs; KT and SC exact up to float64
-rounding of the final division (1e-12)."""
+float64-accumulated oracle on the same inputs (the tensor-core Eucl path, used from 256
+dimensions up, has a stated tolerance of 1e-4; PO_EUCL_EXACT=1 selects the exact kernel);
+KT and SC exact up to float64 rounding of the final division (1e-12)."""
 import numpy as np
 import pytest
 import torch
@@ -14,6 +15,17 @@ from phyloligo_b200 import engine, phylodist, synth
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-6
+RTOL_TC = 1e-4  # stated tolerance of the tensor-core Euclidean path
+
+
+@pytest.fixture(params=["tensor", "exact"])
+def eucl_path(request, monkeypatch):
+    """Run a test once per Euclidean kernel: tensor cores (default from 256 dimensions) and exact."""
+    if request.param == "exact":
+        monkeypatch.setenv("PO_EUCL_EXACT", "1")
+    else:
+        monkeypatch.delenv("PO_EUCL_EXACT", raising=False)
+    return request.param
 
 
 def _gpu_matrix(X, metric, out_dtype=torch.float64, symmetric=True):
@@ -34,17 +46,18 @@ def _assert_close(got, want, rtol=RTOL, atol=0.0):
         (err / np.maximum(np.abs(want), 1e-300)).max(), np.argwhere(bad)[:5].tolist())
 
 
-def test_golden_matrices(distance_golden):
+def test_golden_matrices(distance_golden, eucl_path):
     for name in ("real_k4", "sparse_64", "onehot_16"):
         X = distance_golden[name + "_X"]
         # oracle on the float32-rounded inputs the kernel consumes, float64 accumulation
         X32 = X.astype(np.float32).astype(np.float64)
         for metric in ("Eucl", "JSD"):
             got = _gpu_matrix(X, metric)
-            _assert_close(got, po.pairwise_np(X32, metric), atol=1e-12)
+            tc = metric == "Eucl" and eucl_path == "tensor" and X.shape[1] >= 256
+            _assert_close(got, po.pairwise_np(X32, metric), rtol=RTOL_TC if tc else RTOL, atol=1e-12)
             # and against the reference's own float64 output on the float64 inputs
             ref = distance_golden[name + "_" + metric]
-            assert np.allclose(got, ref, rtol=5e-6, atol=1e-9)
+            assert np.allclose(got, ref, rtol=RTOL_TC if tc else 5e-6, atol=1e-9)
             assert np.array_equal(got, got.T)
             assert (np.diag(got) == 0).all()
     e = np.eye(16)[:6]
@@ -55,11 +68,14 @@ def test_golden_matrices(distance_golden):
 
 @pytest.mark.parametrize("metric", ["Eucl", "JSD", "BC"])
 @pytest.mark.parametrize("pattern,n,length", [("1111", 150, 4000), ("11111", 70, 2000), ("111010011", 66, 3000)])
-def test_float_metrics_vs_fp64_oracle(metric, pattern, n, length):
+def test_float_metrics_vs_fp64_oracle(metric, pattern, n, length, eucl_path):
+    if metric != "Eucl" and eucl_path == "exact":
+        pytest.skip("only Eucl has two kernels")
     X = _profiles(n, length, pattern, seed=31, dtype=np.float32)
     X[3] = 0.0  # an empty contig: all-zero profile
     want = po.pairwise_np(X.astype(np.float64), metric)
-    for out_dtype, rt in ((torch.float64, RTOL), (torch.float32, RTOL)):
+    tol = RTOL_TC if (metric == "Eucl" and eucl_path == "tensor" and X.shape[1] >= 256) else RTOL
+    for out_dtype, rt in ((torch.float64, tol), (torch.float32, tol)):
         got = _gpu_matrix(X, metric, out_dtype).astype(np.float64)
         mask = np.isfinite(want)
         assert np.array_equal(np.isnan(got), np.isnan(want))  # BC of two zero rows: 0/0
@@ -161,3 +177,31 @@ def test_panel_streamer_matches_resident_matrix():
 
         st.run(sink)
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n,dim", [(300, 256), (129, 1024), (200, 4096), (128, 320)])
+def test_tensor_core_euclidean(n, dim, monkeypatch):
+    """tcgen05 Gram path: tolerance 1e-4 (stated), symmetric, exact zero diagonal, identical
+    whichever block computes an entry; near-duplicate rows keep their small distances."""
+    monkeypatch.delenv("PO_EUCL_EXACT", raising=False)
+    rng = np.random.default_rng(dim + n)
+    X = rng.dirichlet(np.full(dim, 0.3), size=n).astype(np.float32)
+    X[5] = X[4] * (1 + 1e-3 * rng.standard_normal(dim)).astype(np.float32)  # near-duplicate pair
+    X[7] = 0.0
+    want = po.pairwise_np(X.astype(np.float64), "Eucl")
+    got = _gpu_matrix(X, "Eucl", torch.float64, symmetric=True)
+    off = ~np.eye(n, dtype=bool)
+    rel = np.abs(got - want)[off] / want[off]
+    print("tensor-core Eucl n=%d dim=%d: max rel err %.3e (near-duplicate pair %.3e)" % (
+        n, dim, rel.max(), abs(got[4, 5] - want[4, 5]) / want[4, 5]))
+    assert rel.max() < RTOL_TC
+    assert (np.diag(got) == 0).all() and np.array_equal(got, got.T)
+    full = _gpu_matrix(X, "Eucl", torch.float64, symmetric=False)
+    assert np.array_equal(full, got)
+    # a block row through the worker API and float32 output
+    Xd = torch.from_numpy(X).cuda()
+    P, aux, d = engine.prepare(Xd, "Eucl")
+    blk = torch.empty((40, n), dtype=torch.float32, device="cuda")
+    engine.distance_block("Eucl", P, aux, d, 70, 110, 0, n, blk, 70, 0)
+    # the float32 epilogue takes a float32 square root of the same float64 d^2
+    assert np.allclose(blk.cpu().numpy(), got[70:110], rtol=2e-7, atol=0)
