@@ -43,6 +43,7 @@ constexpr int GBLOCK_BYTES = GT * GK * 2;     // one operand block: 16 KB
 constexpr int GSTAGE_BYTES = 4 * GBLOCK_BYTES;  // A hi, A lo, B hi, B lo
 constexpr int GSTAGES = 3;
 constexpr int GTHREADS = 128;
+constexpr int GRASTER = 16;             // tile columns per rasterisation chunk
 constexpr float GSCALE = 16384.0f;      // 2^14
 constexpr double GUNSCALE = 1.0 / (16384.0 * 16384.0);
 
@@ -244,6 +245,7 @@ struct GramParams {
     int64_t n;
     int64_t row0, row1, col0, col1;
     int64_t tile_row0, tile_col0;
+    int64_t tiles_r, tiles_c;  // tile grid; CTAs walk it in column chunks of GRASTER tiles (L2 reuse)
     void* out;
     int64_t ld_out, out_row0, out_col0;
     void* mir;
@@ -256,8 +258,14 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
     extern __shared__ __align__(1024) unsigned char gsmem[];
     __shared__ __align__(8) unsigned long long bars[2 * GSTAGES + 1];
     __shared__ uint32_t s_tmem;
-    const int64_t row_base = p.tile_row0 + (int64_t)blockIdx.y * GT;
-    const int64_t col_base = p.tile_col0 + (int64_t)blockIdx.x * GT;
+    // rasterisation: chunks of GRASTER tile columns, all tile rows inside a chunk, so that the
+    // chunk's column operands (GRASTER x 2 MB at 4096 dimensions) stay in L2 while the rows stream
+    const int64_t per_chunk = p.tiles_r * GRASTER;
+    const int64_t chunk = (int64_t)blockIdx.x / per_chunk;
+    const int64_t rem = (int64_t)blockIdx.x - chunk * per_chunk;
+    const int64_t gw = min((int64_t)GRASTER, p.tiles_c - chunk * GRASTER);
+    const int64_t row_base = p.tile_row0 + (rem / gw) * GT;
+    const int64_t col_base = p.tile_col0 + (chunk * GRASTER + rem % gw) * GT;
     if ((p.flags & PO_FLAG_SKIP_LOWER) && col_base + GT <= row_base) return;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -424,12 +432,14 @@ int launch_gram(const void* d_P, const double* d_aux, int64_t n, int64_t dim, in
     p.mir = d_mir; p.ld_mir = ld_mir; p.mir_row0 = mir_row0; p.mir_col0 = mir_col0;
     p.flags = flags;
     const int64_t tr = (row1 - p.tile_row0 + GT - 1) / GT, tc = (col1 - p.tile_col0 + GT - 1) / GT;
-    if (tr > 65535) {
-        set_error("row block too tall: %lld rows (max %d per call)", (long long)(row1 - row0), 65535 * GT);
+    if (tr * tc > 0x7FFFFFFFll) {
+        set_error("block too large: %lld x %lld tiles", (long long)tr, (long long)tc);
         return PO_ERR_UNSUPPORTED;
     }
+    p.tiles_r = tr;
+    p.tiles_c = tc;
     const size_t smem = (size_t)GSTAGES * GSTAGE_BYTES + 1024;
-    dim3 grid((unsigned)tc, (unsigned)tr, 1);
+    dim3 grid((unsigned)(tr * tc), 1, 1);
     LaunchTimer tm(1, stream);
     if (out_dtype == PO_F32) {
         PO_CUDA_CHECK(cudaFuncSetAttribute(gram_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
