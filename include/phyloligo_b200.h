@@ -41,7 +41,15 @@ enum po_status {
 enum po_strand { PO_STRAND_PLUS = 0, PO_STRAND_MINUS = 1, PO_STRAND_BOTH = 2 };
 
 /* -d/--distance choices, bin/phyloligo.py:1010; unpack_distances, bin/phyloligo.py:159-164 */
-enum po_metric { PO_EUCL = 0, PO_JSD = 1, PO_KT = 2, PO_BC = 3, PO_SC = 4 };
+enum po_metric {
+    PO_EUCL = 0, PO_JSD = 1, PO_KT = 2, PO_BC = 3, PO_SC = 4,
+    /* Eucl in the Gram form ||x||^2 + ||y||^2 - 2 x.y on the tensor cores: what the reference's
+     * --large workers compute through sklearn euclidean_distances (bin/phyloligo.py:200-202,
+     * 238-246), stated tolerance 1e-4 relative.  PO_EUCL is the direct sum (a-b)^2 of
+     * phylodist.Eucl (core/phylodist.py:36-41).  Below 256 dimensions, or with
+     * PO_EUCL_EXACT=1 in the environment, PO_EUCL_GRAM runs the PO_EUCL kernel. */
+    PO_EUCL_GRAM = 5
+};
 
 enum po_dtype { PO_F32 = 0, PO_F64 = 1 };
 
@@ -108,10 +116,10 @@ int po_profile_batch(const uint8_t* d_text, const int64_t* d_begin, const int64_
 /*
  * Size in bytes of the prepared operand buffer (the layout po_distance_block consumes)
  * of n profiles of dimension `dim` for `metric`; the caller allocates it.
- *   Eucl      : dim >= 256: centred float16 hi/lo operand blocks for the tensor-core kernel
- *               (n rounded up to 128, dim to 64, 4 bytes per element) + dim float64 column sums;
- *               dim < 256 or PO_EUCL_EXACT=1: as BC
- *   BC        : n rows of dim rounded up to a multiple of 4, float32
+ *   Eucl / BC : n rows of dim rounded up to a multiple of 4, float32
+ *   EuclGram  : centred float16 hi/lo operand blocks for the tensor-core kernel (n rounded up to
+ *               128, dim to 64, 4 bytes per element), float64 column sums, and a float32 copy of
+ *               the profiles for the exact recomputation of cancelling entries
  *   SC        : the same count of int32 (centred doubled average ranks)
  *   KT        : n rows of packed order-relation bit masks, 2 * ceil(dim(dim-1)/2 / 128) * 16 bytes
  *   JSD       : float32 with exact zeros biased to 1e-30, dim rounded up to a multiple of 32
@@ -155,8 +163,8 @@ int po_prepare_profiles(int metric, const void* d_X, int dtype, int64_t n, int64
  *   flags        PO_FLAG_SKIP_LOWER / PO_FLAG_MIRROR exploit symmetry when the
  *                caller's `out` addresses the full matrix (mirrored entries
  *                (c, r) must be addressable).
- * Values: Eucl = sqrt(sum (a-b)^2) (dim >= 256: Gram form on the tensor cores, exact 0 on the
- * diagonal, stated tolerance 1e-4 relative, measured ~1e-6; PO_EUCL_EXACT=1 forces the exact kernel); JSD in nats (core/phylodist.py:22), 0 for
+ * Values: Eucl = sqrt(sum (a-b)^2) (PO_EUCL_GRAM: Gram form on the tensor cores, exact 0 on the
+ * diagonal, stated tolerance 1e-4 relative, measured < 1e-6); JSD in nats (core/phylodist.py:22), 0 for
  * identical rows, ln(2)/2 against an all-zero row; BC = sum|a-b| / sum|a+b|;
  * KT = 1 - (1 - tau_b) (tau_b itself; 0 when a row is constant); SC = 1 - rho
  * (NaN when a row is constant).

@@ -14,7 +14,10 @@ LIB_PATH = os.path.join(PKG_DIR, "lib", "libphyloligo_b200.so")
 
 PO_OK = 0
 STRANDS = {"plus": 0, "minus": 1, "both": 2}
-METRICS = {"Eucl": 0, "JSD": 1, "KT": 2, "BC": 3, "SC": 4}
+METRICS = {"Eucl": 0, "JSD": 1, "KT": 2, "BC": 3, "SC": 4,
+           # Eucl in the Gram form on the tensor cores (what the reference's --large workers compute
+           # through sklearn euclidean_distances, bin/phyloligo.py:200-202, 238-246)
+           "EuclGram": 5}
 PO_F32, PO_F64 = 0, 1
 FLAG_SKIP_LOWER, FLAG_MIRROR = 1, 2
 TILE = 64

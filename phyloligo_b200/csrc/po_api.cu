@@ -194,7 +194,7 @@ int po_profile_batch(const uint8_t* d_text, const int64_t* d_begin, const int64_
 }
 
 int64_t po_prepared_row_bytes(int metric, int64_t dim) {
-    if (metric < PO_EUCL || metric > PO_SC || dim < 1) {
+    if (metric < PO_EUCL || metric > PO_EUCL_GRAM || dim < 1) {
         set_error("po_prepared_row_bytes: bad metric/dim");
         return PO_ERR_ARG;
     }
@@ -202,7 +202,7 @@ int64_t po_prepared_row_bytes(int metric, int64_t dim) {
 }
 
 int64_t po_prepared_bytes(int metric, int64_t n, int64_t dim) {
-    if (metric < PO_EUCL || metric > PO_SC || dim < 1 || n < 0) {
+    if (metric < PO_EUCL || metric > PO_EUCL_GRAM || dim < 1 || n < 0) {
         set_error("po_prepared_bytes: bad metric/n/dim");
         return PO_ERR_ARG;
     }
@@ -211,7 +211,7 @@ int64_t po_prepared_bytes(int metric, int64_t n, int64_t dim) {
 
 int po_prepare_profiles(int metric, const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx,
                         void* d_P, double* d_aux, po_stream_t stream) {
-    if (metric < PO_EUCL || metric > PO_SC) {
+    if (metric < PO_EUCL || metric > PO_EUCL_GRAM) {
         set_error("unknown metric %d", metric);
         return PO_ERR_ARG;
     }
@@ -227,7 +227,7 @@ static int distance_block_checked(int metric, const void* d_P, const double* d_a
                                   int64_t ld_out, int64_t out_row0, int64_t out_col0, void* d_mir, int64_t ld_mir,
                                   int64_t mir_row0, int64_t mir_col0, int out_dtype, unsigned flags,
                                   po_stream_t stream) {
-    if (metric < PO_EUCL || metric > PO_SC) {
+    if (metric < PO_EUCL || metric > PO_EUCL_GRAM) {
         set_error("unknown metric %d", metric);
         return PO_ERR_ARG;
     }

@@ -70,7 +70,7 @@ int launch_distance(int metric, const void* d_P, const double* d_aux, int64_t n,
                     int out_dtype, unsigned flags, cudaStream_t stream);
 
 // Euclidean distances on the tensor cores (po_gram.cu)
-bool eucl_use_gram(int64_t dim);
+bool eucl_use_gram(int metric, int64_t dim);
 int64_t gram_prepared_bytes(int64_t n, int64_t dim);
 int launch_gram_prepare(const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx, void* d_P, double* d_aux,
                         cudaStream_t stream);

@@ -301,7 +301,7 @@ int launch_distance(int metric, const void* d_P, const double* d_aux, int64_t n,
                     void* d_mir, int64_t ld_mir, int64_t mir_row0, int64_t mir_col0,
                     int out_dtype, unsigned flags, cudaStream_t stream) {
     if (row1 <= row0 || col1 <= col0) return PO_OK;
-    if (metric == PO_EUCL && eucl_use_gram(dim))
+    if (eucl_use_gram(metric, dim))
         return launch_gram(d_P, d_aux, n, dim, row0, row1, col0, col1, d_out, ld_out, out_row0, out_col0, d_mir, ld_mir,
                            mir_row0, mir_col0, out_dtype, flags, stream);
     TileParams p;
@@ -315,6 +315,7 @@ int launch_distance(int metric, const void* d_P, const double* d_aux, int64_t n,
     p.mir = d_mir; p.ld_mir = ld_mir; p.mir_row0 = mir_row0; p.mir_col0 = mir_col0;
     p.flags = flags;
     switch (metric) {
+        case PO_EUCL_GRAM:
         case PO_EUCL: return launch_kind<K_EUCL, 64>(p, out_dtype, stream);
         case PO_JSD:
             return launch_jsd(d_P, n, dim, row0, row1, col0, col1, d_out, ld_out, out_row0, out_col0, d_mir, ld_mir,

@@ -18,7 +18,7 @@
 //   * entries whose Gram form cancels by more than 2^8 (n_a + n_b > 256 d^2: near-duplicate
 //     profiles) are recomputed exactly as sum (a-b)^2 by the warp that owns them, from a
 //     float32 copy of the profiles kept next to the operand blocks.
-// Measured error against the float64 oracle is ~1e-8 relative for ordinary pairs and below
+// Measured error against a float64 evaluation is ~1e-8 relative for ordinary pairs and below
 // 5e-5 at the cancellation threshold; the stated tolerance of this path is 1e-4
 // (BASELINE.json north_star).  PO_EUCL_EXACT=1 (or dim < 256) selects
 // the exact CUDA-core kernel of po_distance.cu instead.
@@ -47,7 +47,8 @@ constexpr int GRASTER = 16;             // tile columns per rasterisation chunk
 constexpr float GSCALE = 16384.0f;      // 2^14
 constexpr double GUNSCALE = 1.0 / (16384.0 * 16384.0);
 
-bool eucl_use_gram(int64_t dim) {
+bool eucl_use_gram(int metric, int64_t dim) {
+    if (metric != PO_EUCL_GRAM) return false;
     const char* e = getenv("PO_EUCL_EXACT");
     if (e && e[0] == '1') return false;
     return dim >= 256;

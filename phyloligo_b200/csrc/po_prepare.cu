@@ -42,7 +42,7 @@ int64_t prepared_row_elems(int metric, int64_t dim) {
 int64_t prepared_bytes(int metric, int64_t n, int64_t dim) {
     const int64_t ldp = prepared_row_elems(metric, dim);
     if (metric == PO_JSD) return 3 * ((n + 63) / 64 * 64) * ldp * 4;  // blocked B + doubled A, rows padded to 64
-    if (metric == PO_EUCL && eucl_use_gram(dim)) return gram_prepared_bytes(n, dim);
+    if (eucl_use_gram(metric, dim)) return gram_prepared_bytes(n, dim);
     return n * ldp * 4;
 }
 
@@ -213,6 +213,7 @@ static int launch_prepare_t(int metric, const void* d_X, int64_t n, int64_t dim,
             return PO_OK;
         }
         case PO_EUCL:
+        case PO_EUCL_GRAM:
         case PO_BC: {
             const int want_sum = (metric == PO_BC);
             if (want_sum && !d_aux) {
@@ -268,7 +269,7 @@ static int launch_prepare_t(int metric, const void* d_X, int64_t n, int64_t dim,
 int launch_prepare(int metric, const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx,
                    void* d_P, double* d_aux, cudaStream_t stream) {
     if (n == 0) return PO_OK;
-    if (metric == PO_EUCL && eucl_use_gram(dim) && (dtype == PO_F32 || dtype == PO_F64))
+    if (eucl_use_gram(metric, dim) && (dtype == PO_F32 || dtype == PO_F64))
         return launch_gram_prepare(d_X, dtype, n, dim, ldx, d_P, d_aux, stream);
     if (n > 0x7FFFFFFFll) {
         set_error("too many rows (%lld)", (long long)n);

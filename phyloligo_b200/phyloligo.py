@@ -78,9 +78,16 @@ def compute_unpack(params):
     return i, j, engine.pair_distance(freqi, freqj, distname)
 
 
+def _large_metric(metric):
+    """The reference's --large workers compute Eucl through sklearn's Gram-form
+    euclidean_distances (:200-202, :238-246); here that is the tensor-core kernel."""
+    return "EuclGram" if metric == "Eucl" else metric
+
+
 def distances_loc(output, X, s, metric):
     """output[s] = D(X[s], X) for one block-row slice (reference :195-222)."""
     _check_metric(metric)
+    metric = _large_metric(metric)
     device = engine.require_cuda()
     Xd = torch.from_numpy(np.ascontiguousarray(X)).to(device)
     P, aux, dim = engine.prepare(Xd, metric)
@@ -216,7 +223,7 @@ def compute_distances_device(frequencies, metric="Eucl"):
 
 
 def _stream_to(sink_array, X, metric):
-    streamer = engine.PanelStreamer(X, metric, torch.float32, PANEL_ROWS)
+    streamer = engine.PanelStreamer(X, _large_metric(metric), torch.float32, PANEL_ROWS)
 
     def sink(r0, r1, host):
         sink_array[r0:r1] = host
@@ -245,7 +252,7 @@ def compute_distances_h5py(freq_name, dist_name, metric="Eucl"):
     n = freqs.shape[0]
     X = torch.from_numpy(np.ascontiguousarray(freqs)).to(device)
     with io_formats.Hdf5DatasetWriter(dist_name, "distances", (n, n), np.float32) as writer:
-        streamer = engine.PanelStreamer(X, metric, torch.float32, PANEL_ROWS)
+        streamer = engine.PanelStreamer(X, _large_metric(metric), torch.float32, PANEL_ROWS)
         streamer.run(lambda r0, r1, host: writer.write_rows(r0, host))
     remove_folder(os.path.dirname(freq_name))
 

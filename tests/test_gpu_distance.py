@@ -19,13 +19,14 @@ RTOL_TC = 1e-4  # stated tolerance of the tensor-core Euclidean path
 
 
 @pytest.fixture(params=["tensor", "exact"])
-def eucl_path(request, monkeypatch):
-    """Run a test once per Euclidean kernel: tensor cores (default from 256 dimensions) and exact."""
-    if request.param == "exact":
-        monkeypatch.setenv("PO_EUCL_EXACT", "1")
-    else:
-        monkeypatch.delenv("PO_EUCL_EXACT", raising=False)
+def eucl_path(request):
+    """Run a test once per Euclidean kernel: metric EuclGram (tensor cores from 256 dimensions up,
+    the form of the reference's --large workers) and metric Eucl (the exact direct sum)."""
     return request.param
+
+
+def _eucl_name(metric, eucl_path):
+    return "EuclGram" if (metric == "Eucl" and eucl_path == "tensor") else metric
 
 
 def _gpu_matrix(X, metric, out_dtype=torch.float64, symmetric=True):
@@ -52,7 +53,7 @@ def test_golden_matrices(distance_golden, eucl_path):
         # oracle on the float32-rounded inputs the kernel consumes, float64 accumulation
         X32 = X.astype(np.float32).astype(np.float64)
         for metric in ("Eucl", "JSD"):
-            got = _gpu_matrix(X, metric)
+            got = _gpu_matrix(X, _eucl_name(metric, eucl_path))
             tc = metric == "Eucl" and eucl_path == "tensor" and X.shape[1] >= 256
             _assert_close(got, po.pairwise_np(X32, metric), rtol=RTOL_TC if tc else RTOL, atol=1e-12)
             # and against the reference's own float64 output on the float64 inputs
@@ -76,12 +77,12 @@ def test_float_metrics_vs_fp64_oracle(metric, pattern, n, length, eucl_path):
     want = po.pairwise_np(X.astype(np.float64), metric)
     tol = RTOL_TC if (metric == "Eucl" and eucl_path == "tensor" and X.shape[1] >= 256) else RTOL
     for out_dtype, rt in ((torch.float64, tol), (torch.float32, tol)):
-        got = _gpu_matrix(X, metric, out_dtype).astype(np.float64)
+        got = _gpu_matrix(X, _eucl_name(metric, eucl_path), out_dtype).astype(np.float64)
         mask = np.isfinite(want)
         assert np.array_equal(np.isnan(got), np.isnan(want))  # BC of two zero rows: 0/0
         _assert_close(got[mask], want[mask], rtol=rt, atol=1e-12)
-    full = _gpu_matrix(X, metric, torch.float64, symmetric=False)
-    sym = _gpu_matrix(X, metric, torch.float64, symmetric=True)
+    full = _gpu_matrix(X, _eucl_name(metric, eucl_path), torch.float64, symmetric=False)
+    sym = _gpu_matrix(X, _eucl_name(metric, eucl_path), torch.float64, symmetric=True)
     assert np.array_equal(full, sym, equal_nan=True)  # mirrored tiles are bitwise the computed ones
 
 
@@ -180,28 +181,27 @@ def test_panel_streamer_matches_resident_matrix():
 
 
 @pytest.mark.parametrize("n,dim", [(300, 256), (129, 1024), (200, 4096), (128, 320)])
-def test_tensor_core_euclidean(n, dim, monkeypatch):
+def test_tensor_core_euclidean(n, dim):
     """tcgen05 Gram path: tolerance 1e-4 (stated), symmetric, exact zero diagonal, identical
     whichever block computes an entry; near-duplicate rows keep their small distances."""
-    monkeypatch.delenv("PO_EUCL_EXACT", raising=False)
     rng = np.random.default_rng(dim + n)
     X = rng.dirichlet(np.full(dim, 0.3), size=n).astype(np.float32)
     X[5] = X[4] * (1 + 1e-3 * rng.standard_normal(dim)).astype(np.float32)  # near-duplicate pair
     X[7] = 0.0
     want = po.pairwise_np(X.astype(np.float64), "Eucl")
-    got = _gpu_matrix(X, "Eucl", torch.float64, symmetric=True)
+    got = _gpu_matrix(X, "EuclGram", torch.float64, symmetric=True)
     off = ~np.eye(n, dtype=bool)
     rel = np.abs(got - want)[off] / want[off]
     print("tensor-core Eucl n=%d dim=%d: max rel err %.3e (near-duplicate pair %.3e)" % (
         n, dim, rel.max(), abs(got[4, 5] - want[4, 5]) / want[4, 5]))
     assert rel.max() < RTOL_TC
     assert (np.diag(got) == 0).all() and np.array_equal(got, got.T)
-    full = _gpu_matrix(X, "Eucl", torch.float64, symmetric=False)
+    full = _gpu_matrix(X, "EuclGram", torch.float64, symmetric=False)
     assert np.array_equal(full, got)
     # a block row through the worker API and float32 output
     Xd = torch.from_numpy(X).cuda()
-    P, aux, d = engine.prepare(Xd, "Eucl")
+    P, aux, d = engine.prepare(Xd, "EuclGram")
     blk = torch.empty((40, n), dtype=torch.float32, device="cuda")
-    engine.distance_block("Eucl", P, aux, d, 70, 110, 0, n, blk, 70, 0)
+    engine.distance_block("EuclGram", P, aux, d, 70, 110, 0, n, blk, 70, 0)
     # the float32 epilogue takes a float32 square root of the same float64 d^2
     assert np.allclose(blk.cpu().numpy(), got[70:110], rtol=2e-7, atol=0)

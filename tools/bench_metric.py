@@ -10,8 +10,8 @@ ap.add_argument("--dim", type=int, default=4096)
 ap.add_argument("--exact", action="store_true")
 ap.add_argument("--reps", type=int, default=3)
 args = ap.parse_args()
-if args.exact:
-    os.environ["PO_EUCL_EXACT"] = "1"
+if args.metric == "Eucl" and not args.exact:
+    args.metric = "EuclGram"
 import numpy as np, torch
 from phyloligo_b200 import engine
 from phyloligo_b200._lib import FLAG_MIRROR, FLAG_SKIP_LOWER

@@ -11,7 +11,7 @@ from phyloligo_b200._lib import FLAG_MIRROR, FLAG_SKIP_LOWER
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
-for metric, n, dim in (("JSD", 3000, 256), ("Eucl", 1111, 64), ("BC", 777, 256)):
+for metric, n, dim in (("JSD", 3000, 256), ("Eucl", 1111, 64), ("EuclGram", 1500, 512), ("BC", 777, 256)):
     rng = np.random.default_rng(11)
     X = torch.from_numpy(rng.dirichlet(np.ones(dim), size=n).astype(np.float32)).cuda()
     full = engine.distance_matrix_device(X, metric, torch.float32, symmetric=True)
