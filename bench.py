@@ -78,7 +78,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -167,6 +167,16 @@ def cpu_c_port_rates(seqs_sample, n_profile, n_dist, threads):
     return t_prof / max(1, bases), t_dist / max(1, n * n), dict(profile_bases=bases, profile_s=t_prof, dist_rows=n, dist_s=t_dist)
 
 
+def ncu_traffic(n_contigs):
+    """DRAM bytes per launch of the JSD tile kernel from the committed ncu --set full capture
+    (profiles/r01_traffic.json), when it was taken at this problem size; else None."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["jsd_tile_kernel"]
+        return rec["dram_bytes_per_launch"] if rec["n_contigs"] == n_contigs else None
+    except Exception:
+        return None
+
+
 def whole_job_pairs_per_s(n_contigs, total_bases, s_per_base, s_per_pair):
     pairs = n_contigs * (n_contigs + 1) // 2
     return pairs / (s_per_base * total_bases + s_per_pair * pairs)
@@ -238,7 +248,22 @@ def run_ours(args):
     _lib.load()
 
     n_contigs = max(64, int(round(100_000 * args.scale)))
-    fasta, total_bases = synth.fast_fasta_bytes(n_contigs, args.mean_len, seed=2)
+    # synthetic input: generated once per node (rank 0) and shared through /dev/shm, so that N ranks
+    # do not hold N copies of a multi-GB generator in host memory
+    if world == 1:
+        fasta, total_bases = synth.fast_fasta_bytes(n_contigs, args.mean_len, seed=2)
+    else:
+        shm_dir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        shm_path = os.path.join(shm_dir, "phyloligo_bench_%s_%d_%d.npy" % (os.environ.get("MASTER_PORT", "0"), n_contigs, args.mean_len))
+        meta = torch.zeros(1, dtype=torch.int64, device=device)
+        if rank == 0:
+            fasta0, total_bases = synth.fast_fasta_bytes(n_contigs, args.mean_len, seed=2)
+            np.save(shm_path, fasta0)
+            del fasta0
+            meta[0] = total_bases
+        dist.broadcast(meta, 0)  # also the barrier that makes the file visible
+        total_bases = int(meta.item())
+        fasta = np.load(shm_path, mmap_mode="r")
     pairs_unique = n_contigs * (n_contigs + 1) // 2
 
     # ---- sharding: contiguous record ranges balanced by bytes; triangle-balanced block rows ----
@@ -457,13 +482,16 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(io_bytes[1].item()), "ms_per_step": float(e2e_s.item()) * 1e3},
             "gpu_launches": int(launches),
             "roofline": {
-                "kernel": "distance_tile_kernel<JSD,float>", "bound": "fp32",
+                "kernel": "jsd_tile_kernel<float>", "bound": "fp32",
                 "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+                "frac": achieved / fp32_peak if fp32_peak else None, "traffic": ncu_traffic(n_contigs),
                 "peak_source": "po_microbench FFMA peak measured in this run (MEASURED_PEAKS.json has no FP32-pipe figure)",
                 "flop_convention": "10 flop per dimension per pair (SURVEY.md 8d); D=256",
                 "avg_launch_ms": avg_launch_ms, "launches_timed": int(dist_n),
                 "mufu_lg2_peak_Tops": mufu_peak,
+                "recipe_note": "the kernel spends 12 FP32-pipe operations + 1 MUFU per (pair, dimension) on a "
+                               "cancellation-free series; at 100 % FP32-pipe utilisation that is 10/24 = 0.42 of "
+                               "the 10-flop convention (ncu: sm__pipe_fma_cycles_active 75.6 %, profiles/r01_jsd_tile_ncu_summary.txt)",
             },
             "stages": {
                 "profiling_ms_per_launch": prof_ms / max(1, prof_n),
@@ -491,6 +519,12 @@ def run_ours(args):
             }
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(shm_path)
+            except OSError:
+                pass
         dist.destroy_process_group()
 
 

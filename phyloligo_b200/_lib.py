@@ -20,7 +20,7 @@ METRICS = {"Eucl": 0, "JSD": 1, "KT": 2, "BC": 3, "SC": 4,
            "EuclGram": 5}
 PO_F32, PO_F64 = 0, 1
 FLAG_SKIP_LOWER, FLAG_MIRROR = 1, 2
-TILE = 64
+TILE = 128  # largest kernel tile edge: row panels and rank boundaries are multiples of it
 
 # every symbol include/phyloligo_b200.h declares (tests check the library exports them all)
 EXPORTED = [

@@ -55,6 +55,7 @@ constexpr int JUNROLL = JSD_UNROLL;
 constexpr int JBLOCK_FLOATS = 2048;  // one operand block: 8 KB
 constexpr int JSTAGE_BYTES = 2 * JBLOCK_FLOATS * 4;
 constexpr int JTHREADS = 128;
+constexpr int JRASTER = 128;        // tile columns per rasterisation chunk
 
 // ---- packed f32x2 helpers (sm_100 FADD2 / FMUL2 / FFMA2) ----
 __device__ __forceinline__ u64 pk2(float lo, float hi) {
@@ -160,6 +161,7 @@ struct JsdParams {
     int64_t n;
     int64_t row0, row1, col0, col1;
     int64_t tile_row0, tile_col0;  // first tile origin (multiples of 32 / 64)
+    int64_t tiles_r, tiles_c;      // tile grid, walked in chunks of JRASTER tile columns (L2 reuse)
     void* out;
     int64_t ld_out, out_row0, out_col0;
     void* mir;  // where mirrored tiles go (== out unless the caller gave a separate buffer)
@@ -171,8 +173,14 @@ template <typename OUT_T>
 __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdParams p) {
     extern __shared__ __align__(128) unsigned char jsmem[];
     __shared__ __align__(8) unsigned long long bars[JSTAGES];
-    const int64_t row_base = p.tile_row0 + (int64_t)blockIdx.y * JT_M;
-    const int64_t col_base = p.tile_col0 + (int64_t)blockIdx.x * JT_N;
+    // rasterisation: chunks of JRASTER tile columns, all tile rows inside a chunk, so that the
+    // chunk's column operands (JRASTER x 64 KB at 256 dimensions) stay in L2 while the rows stream
+    const int64_t per_chunk = p.tiles_r * JRASTER;
+    const int64_t chunk = (int64_t)blockIdx.x / per_chunk;
+    const int64_t rem = (int64_t)blockIdx.x - chunk * per_chunk;
+    const int64_t gw = min((int64_t)JRASTER, p.tiles_c - chunk * JRASTER);
+    const int64_t row_base = p.tile_row0 + (rem / gw) * JT_M;
+    const int64_t col_base = p.tile_col0 + (chunk * JRASTER + rem % gw) * JT_N;
     if ((p.flags & PO_FLAG_SKIP_LOWER) && col_base + JT_N <= row_base) return;
 
     const int tid = threadIdx.x;
@@ -353,13 +361,15 @@ int launch_jsd(const void* d_P, int64_t n, int64_t dim, int64_t row0, int64_t ro
     p.mir = d_mir; p.ld_mir = ld_mir; p.mir_row0 = mir_row0; p.mir_col0 = mir_col0;
     p.flags = flags;
     const int64_t tr = (row1 - p.tile_row0 + JT_M - 1) / JT_M, tc = (col1 - p.tile_col0 + JT_N - 1) / JT_N;
-    if (tr > 65535) {
-        set_error("row block too tall: %lld rows (max %d per call)", (long long)(row1 - row0), 65535 * JT_M);
+    if (tr * tc > 0x7FFFFFFFll) {
+        set_error("block too large: %lld x %lld tiles", (long long)tr, (long long)tc);
         return PO_ERR_UNSUPPORTED;
     }
+    p.tiles_r = tr;
+    p.tiles_c = tc;
     const size_t smem = (size_t)JSTAGES * JSTAGE_BYTES;
     static bool attr_set[2] = {false, false};
-    dim3 grid((unsigned)tc, (unsigned)tr, 1);
+    dim3 grid((unsigned)(tr * tc), 1, 1);
     LaunchTimer tm(1, stream);
     if (out_dtype == PO_F32) {
         if (!attr_set[0]) {

@@ -204,7 +204,7 @@ def distance_matrix_device(X, metric, out_dtype=torch.float64, symmetric=True):
     out = torch.empty((n, n), dtype=out_dtype, device=device)
     flags = (FLAG_SKIP_LOWER | FLAG_MIRROR) if symmetric else 0
     # row panels keep every grid dimension inside the launch limits
-    step = 65535 * TILE
+    step = 65535 * 32
     for r0 in range(0, n, step):
         distance_block(metric, P, aux, dim, r0, min(n, r0 + step), 0, n, out, 0, 0, flags)
     if dim < 2 and metric == "KT":

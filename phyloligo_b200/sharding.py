@@ -40,8 +40,9 @@ def record_cuts(lengths, world):
     return cuts
 
 
-def triangle_row_ranges(n, world, align=64):
-    """Row boundaries R[0..world] (multiples of `align`, R[0]=0, R[world]=n) such that the
+def triangle_row_ranges(n, world, align=128):
+    """Row boundaries R[0..world] (multiples of `align` = the largest kernel tile edge, so that no
+    tile straddles two ranks' rows; R[0]=0, R[world]=n) such that the
     number of matrix entries on or right of the diagonal is about equal in every block row
     [R[s], R[s+1]).  The area above row x is x*n - x^2/2, so R[s] = n (1 - sqrt(1 - s/world))."""
     bounds = [0]

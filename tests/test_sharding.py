@@ -30,7 +30,7 @@ def test_triangle_row_ranges(n, world):
     b = sharding.triangle_row_ranges(n, world)
     assert b[0] == 0 and b[-1] == n and len(b) == world + 1
     assert all(y >= x for x, y in zip(b, b[1:]))
-    assert all(x % 64 == 0 for x in b[1:-1])
+    assert all(x % 128 == 0 for x in b[1:-1])
     assert sum(sharding.upper_area(b, s, n) for s in range(world)) == n * (n + 1) // 2
     if n >= 10_000:
         areas = [sharding.upper_area(b, s, n) for s in range(world)]
@@ -71,6 +71,6 @@ def _worker(rank, world, port, n, dim):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 300), (3, 500), (2, 64)])
+@pytest.mark.parametrize("world,n", [(2, 600), (3, 1000), (2, 64)])
 def test_exchange_transposed_gloo(world, n):
     mp.spawn(_worker, args=(world, _free_port(), n, 16), nprocs=world, join=True)
