@@ -14,9 +14,10 @@ already resident in HBM and the matrix left in HBM.  `e2e`: the same pass from
 pinned HOST memory (FASTA bytes -> host index -> H2D -> kernels -> every row
 panel copied back D2H into pinned buffers), all inside the timed region.
 Multi-GPU (torchrun): records are sharded for profiling, profiles all-gathered
-over NCCL; the matrix is split in contiguous block rows with balanced
-upper-triangle area, every rank computes only what lies right of the diagonal
-and sends the transposed off-diagonal blocks to the owners of those rows.
+over NCCL; the matrix is split in 2N block rows, rank s owns rows s and 2N-1-s
+(equal rows, equal upper-triangle area), every rank computes only what lies
+right of the diagonal and sends the transposed off-diagonal blocks to the
+owners of those rows.
 """
 from __future__ import annotations
 
@@ -229,6 +230,16 @@ def run_reference(args):
 # our arm
 # ---------------------------------------------------------------------------
 def run_ours(args):
+    # Libraries (NCCL's version banner, for one) write to stdout; the contract is ONE JSON line there.
+    # Everything but that line goes to stderr: fd 1 points at stderr until the result is printed.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     import torch
     import torch.distributed as dist
     from phyloligo_b200 import _lib, engine, synth
@@ -281,9 +292,10 @@ def run_ours(args):
     shard_bytes = byte_hi - byte_lo
     panel = max(64, (args.panel_rows // 64) * 64)
     symmetric = world == 1
-    bounds = sharding.triangle_row_ranges(n_contigs, world)
-    row_a, row_b = bounds[rank], bounds[rank + 1]
-    rows_owned = row_b - row_a
+    # block rows: rank s owns ranges s and 2*world-1-s (equal rows and equal upper-triangle area)
+    ranges = sharding.paired_row_ranges(n_contigs, world)
+    my_ranges = [i for i in sharding.owned_ranges(ranges, rank, world) if ranges[i][1] > ranges[i][0]]
+    rows_owned = sum(ranges[i][1] - ranges[i][0] for i in my_ranges)
 
     # persistent device buffers
     d_text = torch.empty(shard_bytes + 64, dtype=torch.uint8, device=device)
@@ -298,7 +310,12 @@ def run_ours(args):
         mirror_buf = None
     else:
         matrix = torch.empty((max(1, rows_owned), n_contigs), dtype=torch.float32, device=device)
-        mirror_buf = torch.empty((max(1, n_contigs - row_b), max(1, rows_owned)), dtype=torch.float32, device=device)
+        out_rows, mirror_buf, off = {}, {}, 0
+        for i in my_ranges:  # views of this rank's rows, one per owned range, and the transposed staging
+            a, b = ranges[i]
+            out_rows[i] = matrix[off:off + (b - a)]
+            mirror_buf[i] = torch.empty((max(1, n_contigs - b), b - a), dtype=torch.float32, device=device)
+            off += b - a
     pin_ring = [torch.empty((panel, n_contigs), dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     pin_begin = torch.from_numpy(np.zeros(max(1, n_local), dtype=np.int64)).pin_memory()
@@ -362,15 +379,15 @@ def run_ours(args):
                 d2h_bytes += m * n_contigs * 4
             torch.cuda.current_stream().wait_stream(copy_stream)
             return d2h_bytes
-        # multi-GPU: diagonal block (mirrored in place), then everything right of it with the
-        # transposed tiles going to the exchange buffer; then the one exchange step
-        if rows_owned:
-            engine.distance_block("JSD", P, aux, dim, row_a, row_b, row_a, row_b, matrix, row_a, 0,
-                                  FLAG_SKIP_LOWER | FLAG_MIRROR)
-            if row_b < n_contigs:
-                engine.distance_block("JSD", P, aux, dim, row_a, row_b, row_b, n_contigs, matrix, row_a, 0,
-                                      FLAG_MIRROR, mirror=mirror_buf, mirror_row0=row_b, mirror_col0=row_a)
-        sharding.exchange_transposed(mirror_buf, bounds, rank, world, matrix[:rows_owned] if rows_owned else matrix[:0])
+        # multi-GPU: per owned block row, the diagonal block (mirrored in place), then everything right
+        # of it with the transposed tiles going to the exchange buffer; then the one exchange step
+        for i in my_ranges:
+            a, b = ranges[i]
+            engine.distance_block("JSD", P, aux, dim, a, b, a, b, out_rows[i], a, 0, FLAG_SKIP_LOWER | FLAG_MIRROR)
+            if b < n_contigs:
+                engine.distance_block("JSD", P, aux, dim, a, b, b, n_contigs, out_rows[i], a, 0,
+                                      FLAG_MIRROR, mirror=mirror_buf[i], mirror_row0=b, mirror_col0=a)
+        sharding.exchange_transposed(mirror_buf, ranges, rank, world, out_rows)
         return d2h_panels(matrix, rows_owned) if d2h else 0
 
     def step_resident():
@@ -446,7 +463,7 @@ def run_ours(args):
             for t0_ in range(0, n_contigs, 64):
                 pairs_per_step_computed += (min(n_contigs, t0_ + 64) - t0_) * (n_contigs - t0_)
         else:
-            pairs_per_step_computed = sharding.upper_area(bounds, rank, n_contigs)
+            pairs_per_step_computed = sharding.upper_area(ranges, rank, world, n_contigs)
         launches_per_step = max(1, dist_n // max(1, args.steps))
         avg_launch_ms = dist_ms / max(1, dist_n)
         flop_per_launch = JSD_FLOPS_PER_PAIR * pairs_per_step_computed / launches_per_step
@@ -470,7 +487,7 @@ def run_ours(args):
                 "total_bases": total_bases, "unique_pairs": pairs_unique,
                 "pairs_computed_per_step_rank0": pairs_per_step_computed,
                 "parallelism": "1 GPU, upper triangle + mirror" if world == 1 else
-                               "%d ranks: records sharded, NCCL all-gather of profiles, triangle-balanced block rows, "
+                               "%d ranks: records sharded, NCCL all-gather of profiles, paired block rows (s, 2W-1-s), "
                                "transposed off-diagonal blocks exchanged over NCCL send/recv" % world,
                 "l2": "inputs (%.2f GB text) and outputs (%.1f GB matrix) exceed the 126 MB L2; no flush needed"
                       % (len(fasta) / 1e9, n_contigs * n_contigs * 4 / 1e9),
@@ -517,7 +534,7 @@ def run_ours(args):
                 "c_port": {"value": whole_job_pairs_per_s(n_contigs, total_bases, cspb, cspp), "unit": UNIT,
                            "cores": cores, "note": "multi-threaded C restatement (oracle/oracle.c), same sample sizes x5"},
             }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         if rank == 0:

@@ -25,16 +25,20 @@ def test_record_cuts_balance_and_cover():
     assert sharding.record_cuts([], 4) == [0, 0, 0, 0, 0]
 
 
-@pytest.mark.parametrize("n,world", [(100_000, 8), (30_000, 2), (1000, 4), (130, 8), (64, 3), (1, 2)])
-def test_triangle_row_ranges(n, world):
-    b = sharding.triangle_row_ranges(n, world)
-    assert b[0] == 0 and b[-1] == n and len(b) == world + 1
-    assert all(y >= x for x, y in zip(b, b[1:]))
-    assert all(x % 128 == 0 for x in b[1:-1])
-    assert sum(sharding.upper_area(b, s, n) for s in range(world)) == n * (n + 1) // 2
+@pytest.mark.parametrize("n,world", [(100_000, 8), (30_000, 2), (1000, 4), (130, 8), (64, 3), (1, 2), (100_000, 1)])
+def test_paired_row_ranges(n, world):
+    rg = sharding.paired_row_ranges(n, world)
+    assert len(rg) == 2 * world and rg[0][0] == 0 and rg[-1][1] == n
+    assert all(a <= b for a, b in rg) and all(rg[i][1] == rg[i + 1][0] for i in range(len(rg) - 1))
+    assert all(a % 128 == 0 for a, _ in rg)
+    owners = [sharding.range_owner(i, world) for i in range(2 * world)]
+    assert sorted(owners) == sorted(list(range(world)) * 2)
+    assert sum(sharding.upper_area(rg, r, world, n) for r in range(world)) == n * (n + 1) // 2
     if n >= 10_000:
-        areas = [sharding.upper_area(b, s, n) for s in range(world)]
-        assert max(areas) / (n * (n + 1) / 2 / world) < 1.05
+        areas = [sharding.upper_area(rg, r, world, n) for r in range(world)]
+        rows = [sum(rg[i][1] - rg[i][0] for i in sharding.owned_ranges(rg, r, world)) for r in range(world)]
+        assert max(areas) / (n * (n + 1) / 2 / world) < 1.03       # equal compute
+        assert max(rows) - min(rows) <= 256                        # equal rows (D2H volume)
 
 
 def _free_port():
@@ -43,7 +47,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, dim):
+def _worker(rank, world, port, n, dim, align):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -51,26 +55,23 @@ def _worker(rank, world, port, n, dim):
         rng = np.random.default_rng(3)
         X = rng.dirichlet(np.ones(dim), size=n)
         full = po.pairwise_np(X, "Eucl")
-        bounds = sharding.triangle_row_ranges(n, world)
-        a, b = bounds[rank], bounds[rank + 1]
-        rows = b - a
-        out_rows = torch.full((rows, n), float("nan"), dtype=torch.float64)
-        # what the rank's two kernel launches produce: its rows right of its first row
-        # (diagonal block mirrored locally) and the transposed off-diagonal blocks
-        out_rows[:, a:] = torch.from_numpy(full[a:b, a:])
-        T = torch.from_numpy(np.ascontiguousarray(full[a:b, b:].T))
-        sharding.exchange_transposed(T, bounds, rank, world, out_rows)
-        assert np.array_equal(out_rows.numpy(), full[a:b]), "rank %d assembled a wrong block row" % rank
-        # every rank's rows together are the whole matrix
-        sizes = [bounds[s + 1] - bounds[s] for s in range(world)]
-        gathered = [torch.empty((sizes[s], n), dtype=torch.float64) for s in range(world)]
-        dist.all_gather(gathered, out_rows) if len(set(sizes)) == 1 else None
-        if len(set(sizes)) == 1:
-            assert np.array_equal(torch.cat(gathered).numpy(), full)
+        ranges = sharding.paired_row_ranges(n, world, align=align)
+        out_rows, T = {}, {}
+        for i in sharding.owned_ranges(ranges, rank, world):
+            a, b = ranges[i]
+            # what the rank's two kernel launches per range produce: its rows from the diagonal block
+            # rightwards (diagonal block mirrored locally) and the transposed off-diagonal blocks
+            out_rows[i] = torch.full((b - a, n), float("nan"), dtype=torch.float64)
+            out_rows[i][:, a:] = torch.from_numpy(full[a:b, a:])
+            T[i] = torch.from_numpy(np.ascontiguousarray(full[a:b, b:].T))
+        sharding.exchange_transposed(T, ranges, rank, world, out_rows)
+        for i, rows in out_rows.items():
+            a, b = ranges[i]
+            assert np.array_equal(rows.numpy(), full[a:b]), "rank %d assembled a wrong block row %d" % (rank, i)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 600), (3, 1000), (2, 64)])
-def test_exchange_transposed_gloo(world, n):
-    mp.spawn(_worker, args=(world, _free_port(), n, 16), nprocs=world, join=True)
+@pytest.mark.parametrize("world,n,align", [(2, 600, 128), (3, 1000, 128), (2, 64, 128), (3, 333, 16)])
+def test_exchange_transposed_gloo(world, n, align):
+    mp.spawn(_worker, args=(world, _free_port(), n, 16, align), nprocs=world, join=True)
