@@ -278,7 +278,7 @@ def run_ours(args):
     pairs_unique = n_contigs * (n_contigs + 1) // 2
 
     # ---- sharding: contiguous record ranges balanced by bytes; triangle-balanced block rows ----
-    from phyloligo_b200 import sharding
+    from phyloligo_b200 import multigpu, sharding
     begin_all, end_all = engine.fasta_index(fasta)
     assert begin_all.shape[0] == n_contigs
     cuts = sharding.record_cuts(end_all - begin_all, world)
@@ -294,8 +294,7 @@ def run_ours(args):
     symmetric = world == 1
     # block rows: rank s owns ranges s and 2*world-1-s (equal rows and equal upper-triangle area)
     ranges = sharding.paired_row_ranges(n_contigs, world)
-    my_ranges = [i for i in sharding.owned_ranges(ranges, rank, world) if ranges[i][1] > ranges[i][0]]
-    rows_owned = sum(ranges[i][1] - ranges[i][0] for i in my_ranges)
+    rows_owned = sum(ranges[i][1] - ranges[i][0] for i in sharding.owned_ranges(ranges, rank, world))
 
     # persistent device buffers
     d_text = torch.empty(shard_bytes + 64, dtype=torch.uint8, device=device)
@@ -307,15 +306,11 @@ def run_ours(args):
     gathered = torch.empty((world * n_max, DIM), dtype=torch.float32, device=device) if world > 1 else None
     if symmetric:
         matrix = torch.empty((n_contigs, n_contigs), dtype=torch.float32, device=device)
-        mirror_buf = None
+        job = None
     else:
-        matrix = torch.empty((max(1, rows_owned), n_contigs), dtype=torch.float32, device=device)
-        out_rows, mirror_buf, off = {}, {}, 0
-        for i in my_ranges:  # views of this rank's rows, one per owned range, and the transposed staging
-            a, b = ranges[i]
-            out_rows[i] = matrix[off:off + (b - a)]
-            mirror_buf[i] = torch.empty((max(1, n_contigs - b), b - a), dtype=torch.float32, device=device)
-            off += b - a
+        # this rank's rows; the other ranks' transposed tiles land in them over NVLink (peer memory)
+        job = multigpu.BlockRows(n_contigs, torch.float32, rank, world)
+        matrix = job.matrix
     pin_ring = [torch.empty((panel, n_contigs), dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     pin_begin = torch.from_numpy(np.zeros(max(1, n_local), dtype=np.int64)).pin_memory()
@@ -379,15 +374,9 @@ def run_ours(args):
                 d2h_bytes += m * n_contigs * 4
             torch.cuda.current_stream().wait_stream(copy_stream)
             return d2h_bytes
-        # multi-GPU: per owned block row, the diagonal block (mirrored in place), then everything right
-        # of it with the transposed tiles going to the exchange buffer; then the one exchange step
-        for i in my_ranges:
-            a, b = ranges[i]
-            engine.distance_block("JSD", P, aux, dim, a, b, a, b, out_rows[i], a, 0, FLAG_SKIP_LOWER | FLAG_MIRROR)
-            if b < n_contigs:
-                engine.distance_block("JSD", P, aux, dim, a, b, b, n_contigs, out_rows[i], a, 0,
-                                      FLAG_MIRROR, mirror=mirror_buf[i], mirror_row0=b, mirror_col0=a)
-        sharding.exchange_transposed(mirror_buf, ranges, rank, world, out_rows)
+        # multi-GPU: per owned block row the diagonal block (mirrored in place) and the blocks right of
+        # it, whose transposed tiles the kernel stores into the owning rank's rows (multigpu.BlockRows)
+        job.compute("JSD", P, aux, dim)
         return d2h_panels(matrix, rows_owned) if d2h else 0
 
     def step_resident():
@@ -488,7 +477,8 @@ def run_ours(args):
                 "pairs_computed_per_step_rank0": pairs_per_step_computed,
                 "parallelism": "1 GPU, upper triangle + mirror" if world == 1 else
                                "%d ranks: records sharded, NCCL all-gather of profiles, paired block rows (s, 2W-1-s), "
-                               "transposed off-diagonal blocks exchanged over NCCL send/recv" % world,
+                               "transposed off-diagonal tiles %s" % (world, "stored by the tile kernel into the owner's rows over NVLink "
+                               "(CUDA IPC peer memory)" if job.peers is not None else "exchanged over NCCL send/recv"),
                 "l2": "inputs (%.2f GB text) and outputs (%.1f GB matrix) exceed the 126 MB L2; no flush needed"
                       % (len(fasta) / 1e9, n_contigs * n_contigs * 4 / 1e9),
                 "e2e_sink": "row panels of %d rows copied D2H into a 2-slot pinned ring (discard sink)" % panel,
@@ -536,6 +526,7 @@ def run_ours(args):
             }
         emit(line)
     if world > 1:
+        job.close()
         dist.barrier()
         if rank == 0:
             try:

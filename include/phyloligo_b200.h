@@ -188,6 +188,20 @@ int po_distance_block_ex(int metric, const void* d_P, const double* d_aux, int64
                          void* d_mirror, int64_t ld_mirror, int64_t mirror_row0, int64_t mirror_col0,
                          int out_dtype, unsigned flags, po_stream_t stream);
 
+/*
+ * Peer memory for the multi-GPU distance stage (one process per GPU on one node).  A rank
+ * exports the buffer that holds its block rows; the other ranks open it and pass the peer
+ * address as `d_mirror` of po_distance_block_ex, so that the transposed off-diagonal tiles are
+ * stored straight into their owner's rows over NVLink while the tile kernel runs -- the exchange
+ * step costs no staging buffer and no separate transfer.
+ *   po_ipc_export : 64-byte CUDA IPC handle of the allocation containing d_ptr, and d_ptr's offset in it
+ *   po_ipc_open   : map a peer's allocation into this process (peer access is enabled lazily)
+ *   po_ipc_close  : unmap it
+ */
+int po_ipc_export(const void* d_ptr, void* h_handle64, int64_t* offset);
+int po_ipc_open(const void* h_handle64, void** d_base);
+int po_ipc_close(void* d_base);
+
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t po_launch_count(void);
 

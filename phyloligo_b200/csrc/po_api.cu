@@ -268,6 +268,51 @@ int po_distance_block_ex(int metric, const void* d_P, const double* d_aux, int64
                                   out_col0, d_mirror, ld_mirror, mirror_row0, mirror_col0, out_dtype, flags, stream);
 }
 
+int po_ipc_export(const void* d_ptr, void* h_handle64, int64_t* offset) {
+    if (!d_ptr || !h_handle64 || !offset) {
+        set_error("po_ipc_export: NULL argument");
+        return PO_ERR_ARG;
+    }
+    // base of the allocation that contains d_ptr (cuMemGetAddressRange, through the runtime's entry-point lookup)
+    typedef int (*get_range_fn)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PO_CUDA_CHECK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+        set_error("po_ipc_export: cuMemGetAddressRange is not available");
+        return PO_ERR_CUDA;
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    const int rc = reinterpret_cast<get_range_fn>(fn)(&base, &size, (unsigned long long)(uintptr_t)d_ptr);
+    if (rc != 0) {
+        set_error("po_ipc_export: cuMemGetAddressRange failed (%d)", rc);
+        return PO_ERR_CUDA;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    PO_CUDA_CHECK(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base)));
+    memcpy(h_handle64, &h, 64);
+    *offset = (int64_t)((unsigned long long)(uintptr_t)d_ptr - base);
+    return PO_OK;
+}
+
+int po_ipc_open(const void* h_handle64, void** d_base) {
+    if (!h_handle64 || !d_base) {
+        set_error("po_ipc_open: NULL argument");
+        return PO_ERR_ARG;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle64, 64);
+    PO_CUDA_CHECK(cudaIpcOpenMemHandle(d_base, h, cudaIpcMemLazyEnablePeerAccess));
+    return PO_OK;
+}
+
+int po_ipc_close(void* d_base) {
+    if (d_base) PO_CUDA_CHECK(cudaIpcCloseMemHandle(d_base));
+    return PO_OK;
+}
+
 int64_t po_launch_count(void) { return g_launches.load(); }
 
 int po_timing_enable(int on) {

@@ -177,9 +177,11 @@ def prepare(X, metric):
 
 
 def distance_block(metric, P, aux, dim, row0, row1, col0, col1, out, out_row0, out_col0, flags=0,
-                   mirror=None, mirror_row0=0, mirror_col0=0):
+                   mirror=None, mirror_row0=0, mirror_col0=0, mirror_ld=None):
     """po_distance_block into the device tensor `out` (2-D, float32 or float64).  With
-    `mirror` (same dtype) the mirrored tiles go to mirror[c - mirror_row0, r - mirror_col0]."""
+    `mirror` the mirrored tiles go to mirror[c - mirror_row0, r - mirror_col0]: a tensor of the
+    output's dtype, or a raw device address (int, e.g. a peer GPU's rows opened with
+    PeerRows) together with its row pitch `mirror_ld` in elements."""
     lib = _lib.load()
     n = int(P.shape[0])
     dt = PO_F32 if out.dtype == torch.float32 else PO_F64
@@ -187,13 +189,56 @@ def distance_block(metric, P, aux, dim, row0, row1, col0, col1, out, out_row0, o
         rc = lib.po_distance_block(METRICS[metric], _ptr(P), _ptr(aux), n, dim, row0, row1, col0, col1,
                                    _ptr(out), int(out.stride(0)), out_row0, out_col0, dt, flags, _stream())
     else:
-        if mirror.dtype != out.dtype:
-            raise PhyloligoError("mirror buffer must have the dtype of the output")
+        if isinstance(mirror, torch.Tensor):
+            if mirror.dtype != out.dtype:
+                raise PhyloligoError("mirror buffer must have the dtype of the output")
+            mptr, mld = _ptr(mirror), int(mirror.stride(0))
+        else:
+            mptr, mld = C.c_void_p(int(mirror)), int(mirror_ld)
         rc = lib.po_distance_block_ex(METRICS[metric], _ptr(P), _ptr(aux), n, dim, row0, row1, col0, col1,
                                       _ptr(out), int(out.stride(0)), out_row0, out_col0,
-                                      _ptr(mirror), int(mirror.stride(0)), mirror_row0, mirror_col0, dt, flags,
-                                      _stream())
+                                      mptr, mld, mirror_row0, mirror_col0, dt, flags, _stream())
     _lib.check(rc, "po_distance_block")
+
+
+class PeerRows:
+    """The block-row buffers of all ranks of one node, mapped into this process (CUDA IPC).
+
+    Every rank passes the tensor that holds its rows; after construction `address(rank)` is the
+    device address of that rank's buffer as seen from here, usable as the `mirror` of
+    distance_block.  Collective over the default process group (all_gather_object)."""
+
+    def __init__(self, local_rows, rank, world):
+        import torch.distributed as dist
+        lib = _lib.load()
+        handle = (C.c_ubyte * 64)()
+        off = C.c_int64()
+        _lib.check(lib.po_ipc_export(_ptr(local_rows), handle, C.byref(off)), "po_ipc_export")
+        mine = (bytes(handle), int(off.value), torch.cuda.current_device())
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        self.local = local_rows
+        self.rank = rank
+        self._bases = {}
+        self._addr = {}
+        for r, (h, offset, dev) in enumerate(everyone):
+            if r == rank:
+                self._addr[r] = local_rows.data_ptr()
+                continue
+            base = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(h)
+            _lib.check(lib.po_ipc_open(buf, C.byref(base)), "po_ipc_open")
+            self._bases[r] = base
+            self._addr[r] = int(base.value) + offset
+
+    def address(self, rank):
+        return self._addr[rank]
+
+    def close(self):
+        lib = _lib.load()
+        for base in self._bases.values():
+            lib.po_ipc_close(base)
+        self._bases = {}
 
 
 def distance_matrix_device(X, metric, out_dtype=torch.float64, symmetric=True):

@@ -1,0 +1,121 @@
+"""The distance stage on the GPUs of one node: one process per GPU, paired block rows.
+
+The reference splits the matrix in block rows over its workers and computes every
+entry of a block row (``gen_even_slices``, bin/phyloligo.py:424, 516; workers
+``distances_loc`` :195 / ``distances_h5py`` :233).  Here rank s owns block rows s and
+2W-1-s (``sharding.paired_row_ranges``), computes only the tiles on or right of the
+diagonal, and every off-diagonal tile is stored twice by the CTA that computed it:
+into this rank's rows, and transposed into the rows of the rank that owns the
+mirrored entries.
+
+exchange = "peer" (default on NVLink boxes): the owners' row buffers are mapped into
+every process with CUDA IPC (``engine.PeerRows``) and the tile kernel's mirror stores
+go straight to peer memory over NVLink / NVSwitch while the tile math runs -- the
+exchange is fused into the compute kernel, there is no staging buffer and no
+transfer step.  One tiny all-reduce at the end is the device-side barrier that makes
+every rank's rows complete.
+
+exchange = "nccl": the transposed tiles go to a local staging buffer and one
+``batch_isend_irecv`` step moves them (``sharding.exchange_transposed``); this is the
+path the gloo CPU tests exercise and the fallback when peer mapping is unavailable.
+
+Both give bit for bit the rows of a single-GPU run: same kernels, same tile grid.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import engine, sharding
+from ._lib import FLAG_MIRROR, FLAG_SKIP_LOWER
+
+
+def default_exchange():
+    return os.environ.get("PO_EXCHANGE", "peer")
+
+
+class BlockRows:
+    """This rank's paired block rows of the symmetric n x n matrix, resident on the device.
+
+    matrix       [rows_owned x n] tensor: the owned ranges stacked in ascending order
+    out_rows[i]  view of the rows of owned range i
+    """
+
+    def __init__(self, n, out_dtype, rank, world, exchange=None, device=None):
+        self.n, self.rank, self.world = int(n), rank, world
+        self.out_dtype = out_dtype
+        self.device = device or engine.require_cuda()
+        self.exchange = exchange or default_exchange()
+        self.ranges = sharding.paired_row_ranges(self.n, world)
+        self.offsets = sharding.range_offsets(self.ranges, world)
+        self.my_ranges = [i for i in sharding.owned_ranges(self.ranges, rank, world)
+                          if self.ranges[i][1] > self.ranges[i][0]]
+        self.rows_owned = sum(self.ranges[i][1] - self.ranges[i][0] for i in self.my_ranges)
+        self.matrix = torch.empty((max(1, self.rows_owned), self.n), dtype=out_dtype, device=self.device)
+        self.out_rows = {}
+        for i in self.my_ranges:
+            a, b = self.ranges[i]
+            self.out_rows[i] = self.matrix[self.offsets[i]:self.offsets[i] + (b - a)]
+        self.esize = self.matrix.element_size()
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.peers = None
+        self.staging = None
+        if world > 1 and self.exchange == "peer":
+            self.peers = engine.PeerRows(self.matrix, rank, world)
+        elif world > 1:
+            self.staging = {}
+            for i in self.my_ranges:
+                a, b = self.ranges[i]
+                self.staging[i] = torch.empty((max(1, self.n - b), b - a), dtype=out_dtype, device=self.device)
+
+    def close(self):
+        if self.peers is not None:
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier()  # nobody unmaps while a peer may still be storing
+            self.peers.close()
+            self.peers = None
+
+    def _device_barrier(self):
+        """Stream-ordered barrier over the ranks: the all-reduce on a rank completes only after every
+        rank has reached it on its stream, i.e. after every rank's tile kernels (and their peer stores,
+        which are performed by kernel completion) are done."""
+        if self.world > 1:
+            dist.all_reduce(self._flag)
+
+    def upper_area(self):
+        return sharding.upper_area(self.ranges, self.rank, self.world, self.n)
+
+    def compute(self, metric, P, aux, dim):
+        """Launch this rank's tiles; on return (in stream order) `matrix` holds its complete rows."""
+        n = self.n
+        if self.peers is not None:
+            self._device_barrier()  # the consumers of the previous result are done with the rows
+        for i in self.my_ranges:
+            a, b = self.ranges[i]
+            rows = self.out_rows[i]
+            engine.distance_block(metric, P, aux, dim, a, b, a, b, rows, a, 0, FLAG_SKIP_LOWER | FLAG_MIRROR)
+            if b >= n:
+                continue
+            if self.staging is not None:
+                engine.distance_block(metric, P, aux, dim, a, b, b, n, rows, a, 0, FLAG_MIRROR,
+                                      mirror=self.staging[i], mirror_row0=b, mirror_col0=a)
+                continue
+            # one launch per block right of the diagonal; its transposed tiles are stored into the
+            # rows of the rank that owns that range (local or peer address, row pitch n)
+            for q in range(i + 1, len(self.ranges)):
+                aq, bq = self.ranges[q]
+                if bq <= aq:
+                    continue
+                owner = sharding.range_owner(q, self.world)
+                base = self.matrix.data_ptr() if owner == self.rank else self.peers.address(owner)
+                addr = base + self.offsets[q] * n * self.esize
+                engine.distance_block(metric, P, aux, dim, a, b, aq, bq, rows, a, 0, FLAG_MIRROR,
+                                      mirror=addr, mirror_row0=aq, mirror_col0=0, mirror_ld=n)
+        if self.peers is not None:
+            self._device_barrier()
+        elif self.world > 1:
+            sharding.exchange_transposed(self.staging, self.ranges, self.rank, self.world, self.out_rows)
+        return self.matrix

@@ -116,3 +116,14 @@ def exchange_transposed(T, ranges, rank, world, out_rows, group=None):
         out_rows[q][:, a:b].copy_(buf)
     assert all(i in mine for i in out_rows)
     return out_rows
+
+
+def range_offsets(ranges, world):
+    """Row offset of every range inside its owner's stacked row buffer (owned ranges in ascending order)."""
+    offsets = [0] * len(ranges)
+    for rank in range(world):
+        off = 0
+        for i in owned_ranges(ranges, rank, world):
+            offsets[i] = off
+            off += ranges[i][1] - ranges[i][0]
+    return offsets

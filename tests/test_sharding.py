@@ -75,3 +75,14 @@ def _worker(rank, world, port, n, dim, align):
 @pytest.mark.parametrize("world,n,align", [(2, 600, 128), (3, 1000, 128), (2, 64, 128), (3, 333, 16)])
 def test_exchange_transposed_gloo(world, n, align):
     mp.spawn(_worker, args=(world, _free_port(), n, 16, align), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("n,world", [(100_000, 8), (3000, 2), (130, 8), (1, 2)])
+def test_range_offsets_stack_the_owned_ranges(n, world):
+    rg = sharding.paired_row_ranges(n, world)
+    off = sharding.range_offsets(rg, world)
+    for rank in range(world):
+        expect = 0
+        for i in sharding.owned_ranges(rg, rank, world):
+            assert off[i] == expect
+            expect += rg[i][1] - rg[i][0]
