@@ -202,6 +202,17 @@ int po_ipc_export(const void* d_ptr, void* h_handle64, int64_t* offset);
 int po_ipc_open(const void* h_handle64, void** d_base);
 int po_ipc_close(void* d_base);
 
+/*
+ * Text matrix writer on the host -- replaces np.savetxt(path, M, delimiter="\t") at
+ * bin/phyloligo.py:1059-1066 (the -o distance matrix and the -q frequency file): "%.18e"
+ * fields of the float64 value of every entry, tab separated, '\n' rows, no header; nan / inf /
+ * -inf spelled as Python spells them.  h_data is a host matrix [rows x cols], row pitch ld
+ * elements, dtype PO_F32 or PO_F64.  Row blocks are formatted by `threads` host threads
+ * (<= 0 picks the hardware concurrency) and written in order.
+ */
+int po_savetxt_host(const char* path, const void* h_data, int64_t rows, int64_t cols, int64_t ld,
+                    int dtype, int threads);
+
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t po_launch_count(void);
 

@@ -173,6 +173,7 @@ template <typename OUT_T>
 __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdParams p) {
     extern __shared__ __align__(128) unsigned char jsmem[];
     __shared__ __align__(8) unsigned long long bars[JSTAGES];
+    __shared__ unsigned done_warps[JSTAGES];  // warps that have finished reading a stage
     // rasterisation: chunks of JRASTER tile columns, all tile rows inside a chunk, so that the
     // chunk's column operands (JRASTER x 64 KB at 256 dimensions) stay in L2 while the rows stream
     const int64_t per_chunk = p.tiles_r * JRASTER;
@@ -193,7 +194,10 @@ __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdP
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < JSTAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+        for (int s = 0; s < JSTAGES; ++s) {
+            mbar_init(bar0 + 8 * s, 1);
+            done_warps[s] = 0;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -314,9 +318,16 @@ __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdP
                 t[i][2 * j + 1] += (double)c1;
                 c2[i][j] = 0ull;
             }
-        __syncthreads();  // every thread is done reading stage s
-        if (tid == 0 && ch + JSTAGES < nchunks) issue(ch + JSTAGES);
+        // Stage s is refilled by whichever warp finishes reading it last: no block-wide barrier in the
+        // chunk loop, the warps drift by up to JSTAGES - 1 chunks.
+        __syncwarp();
+        if ((tid & 31) == 0 && ch + JSTAGES < nchunks) {
+            __threadfence_block();
+            // the counter only grows: every JTHREADS / 32-th arrival is the last warp of a round
+            if (atomicAdd(&done_warps[s], 1u) % (JTHREADS / 32) == JTHREADS / 32 - 1) issue(ch + JSTAGES);
+        }
     }
+    __syncthreads();  // the epilogue reuses the ring as the tile buffer
 
     // ---- epilogue: stage the tile in shared memory, then coalesced stores (and the mirror) ----
     constexpr int TP = JT_N + 1;

@@ -22,8 +22,22 @@ UNDEF = 0xFFFFFFFFFFFFFFFF
 _SIG = b"\x89HDF\r\n\x1a\n"
 
 
-def savetxt(path, arr):
-    np.savetxt(path, arr, delimiter="\t")
+def savetxt(path, arr, threads=0):
+    """``np.savetxt(path, arr, delimiter="\\t")`` (reference bin/phyloligo.py:1059-1066) through the
+    library's threaded host writer (po_savetxt_host): same bytes, without the per-entry Python loop."""
+    from . import _lib
+    arr = np.asarray(arr)
+    if arr.dtype not in (np.float32, np.float64):
+        arr = arr.astype(np.float64)  # an all-zero profile matrix is int in the reference; '%.18e' prints the same
+    if arr.ndim == 1:
+        arr = arr.reshape(-1, 1)  # savetxt writes a 1-D array one value per line
+    if arr.ndim != 2:
+        raise ValueError("savetxt expects a 1-D or 2-D array")
+    arr = np.ascontiguousarray(arr)
+    lib = _lib.load()
+    rc = lib.po_savetxt_host(os.fsencode(path), arr.ctypes.data, arr.shape[0], arr.shape[1], arr.shape[1],
+                             _lib.PO_F32 if arr.dtype == np.float32 else _lib.PO_F64, int(threads))
+    _lib.check(rc, "po_savetxt_host")
 
 
 def read_numpy(path):
@@ -143,6 +157,18 @@ class Hdf5DatasetWriter:
         if self.nbytes:
             self.mm = np.memmap(path, dtype=self.dtype, mode="r+", offset=self.data_off, shape=self.shape)
 
+    @classmethod
+    def attach(cls, path, name):
+        """Open the data region of an existing one-dataset file for in-place row writes (the ranks
+        of a multi-GPU run all fill the file rank 0 created)."""
+        self = cls.__new__(cls)
+        shape, dtype, addr = dataset_location(path, name)
+        self.path, self.shape, self.dtype = path, shape, np.dtype(dtype)
+        self.data_off = addr
+        self.nbytes = int(np.prod(shape, dtype=np.int64)) * self.dtype.itemsize
+        self.mm = np.memmap(path, dtype=self.dtype, mode="r+", offset=addr, shape=shape) if self.nbytes else None
+        return self
+
     def write_rows(self, row0, block):
         self.mm[row0:row0 + block.shape[0]] = block
 
@@ -228,6 +254,15 @@ def _find_dataset(buf, name):
 def read_hdf5(path, name):
     """Read a contiguous float32/float64 dataset written by write_hdf5 (or any file
     using the same classic layout)."""
+    shape, dtype, addr = dataset_location(path, name)
+    n = int(np.prod(shape, dtype=np.int64))
+    if n == 0:
+        return np.zeros(shape, dtype=dtype)
+    return np.array(np.memmap(path, dtype=dtype, mode="r", offset=addr, shape=shape))
+
+
+def dataset_location(path, name):
+    """(shape, dtype, byte offset of the data) of a contiguous dataset."""
     buf = np.memmap(path, dtype=np.uint8, mode="r")
     oh = _find_dataset(buf, name)
     shape = dtype = None
@@ -249,7 +284,4 @@ def read_hdf5(path, name):
             addr, size = struct.unpack_from("<QQ", data, 2)
     if shape is None or dtype is None or addr is None:
         raise ValueError("incomplete dataset header")
-    n = int(np.prod(shape, dtype=np.int64))
-    if n == 0:
-        return np.zeros(shape, dtype=dtype)
-    return np.array(np.memmap(path, dtype=dtype, mode="r", offset=addr, shape=shape))
+    return shape, dtype, int(addr)

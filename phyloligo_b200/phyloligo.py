@@ -29,7 +29,7 @@ import numpy as np
 import torch
 
 from . import engine, io_formats, phylodist
-from ._lib import PhyloligoError, METRICS
+from ._lib import PhyloligoError, METRICS, TILE
 
 PANEL_ROWS = 4096
 
@@ -39,6 +39,41 @@ def remove_folder(folder):
         shutil.rmtree(folder)
     except Exception:
         print("Failed to delete folder: {}".format(folder))
+
+
+# ---------------------------------------------------------------------------
+# one process per GPU (torchrun): the reference's n_jobs workers become the ranks of one node
+# ---------------------------------------------------------------------------
+def ranks():
+    """(rank, world) of this process.  Under torchrun (WORLD_SIZE > 1) the NCCL process group is
+    created on first use, one GPU per rank; a plain ``python phyloligo.py`` run is (0, 1)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), dist.get_world_size()
+
+
+def _barrier():
+    if ranks()[1] > 1:
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+
+
+def _broadcast_str(value):
+    """rank 0's string on every rank (temp-dir names must agree)."""
+    if ranks()[1] == 1:
+        return value
+    import torch.distributed as dist
+    box = [value]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
 
 
 # ---------------------------------------------------------------------------
@@ -144,6 +179,9 @@ def _read_genome(genome):
 
 
 def _profile_file(genome, pattern, strand, want):
+    rank, world = ranks()
+    if world > 1:
+        return _profile_file_sharded(genome, pattern, strand, want, rank, world)
     text = _read_genome(genome)
     begin, end = engine.fasta_index(text)
     if begin.shape[0] == 0:
@@ -151,6 +189,36 @@ def _profile_file(genome, pattern, strand, want):
         return None, 0, dim
     res = engine.profile_text(text, str(pattern), strand, want, begin, end)
     return res, int(begin.shape[0]), None
+
+
+def _profile_file_sharded(genome, pattern, strand, want, rank, world):
+    """Every rank profiles a contiguous, byte-balanced range of the records (the reference fans the
+    sequences out to its workers, :868, :913, :967) and one NCCL all-gather gives every rank the
+    whole (N, 4^k) matrix."""
+    import torch.distributed as dist
+    from . import sharding
+    (key,) = want
+    text = np.memmap(genome, dtype=np.uint8, mode="r") if os.path.getsize(genome) else np.zeros(0, np.uint8)
+    begin, end = engine.fasta_index(text, threads=max(1, (os.cpu_count() or 1) // world))
+    n = int(begin.shape[0])
+    _, _, dim = engine._lib.pattern_info(str(pattern))
+    if n == 0:
+        return None, 0, dim
+    cuts = sharding.record_cuts(end - begin, world)
+    lo, hi = cuts[rank], cuts[rank + 1]
+    n_max = max(cuts[r + 1] - cuts[r] for r in range(world))
+    dtype = torch.float64 if key == "freq64" else torch.float32
+    device = engine.require_cuda()
+    shard = torch.zeros((n_max, dim), dtype=dtype, device=device)
+    if hi > lo:
+        byte_lo, byte_hi = int(begin[lo]), int(end[hi - 1])
+        res = engine.profile_text(np.ascontiguousarray(text[byte_lo:byte_hi]), str(pattern), strand, want,
+                                  begin[lo:hi] - byte_lo, end[lo:hi] - byte_lo)
+        shard[:hi - lo].copy_(res[key])
+    gathered = torch.empty((world * n_max, dim), dtype=dtype, device=device)
+    dist.all_gather_into_tensor(gathered, shard)
+    full = torch.cat([gathered[r * n_max:r * n_max + cuts[r + 1] - cuts[r]] for r in range(world)], dim=0)
+    return {key: full}, n, None
 
 
 def compute_frequencies_device(genome, pattern, strand):
@@ -161,18 +229,27 @@ def compute_frequencies_device(genome, pattern, strand):
     return res["freq64"].cpu().numpy()
 
 
+def _shared_tempdir(workdir):
+    """A temp dir under workdir created by rank 0, same name on every rank."""
+    rank, _ = ranks()
+    return _broadcast_str(tempfile.mkdtemp(dir=workdir) if rank == 0 else None)
+
+
 def compute_frequencies_memmap(genome, pattern, strand, workdir):
     """float32 memmap 'frequencies' in a temp dir under workdir (reference :879-916)."""
-    folder = tempfile.mkdtemp(dir=workdir)
+    rank, _ = ranks()
+    folder = _shared_tempdir(workdir)
     freq_name = os.path.join(folder, "frequencies")
     res, n, dim = _profile_file(genome, pattern, strand, ("freq32",))
     if res is None:
         raise PhyloligoError("no FASTA record in {}".format(genome))
     f32 = res["freq32"]
-    frequencies = np.memmap(freq_name, dtype=np.float32, shape=tuple(f32.shape), mode="w+")
-    frequencies[:] = f32.cpu().numpy()
-    frequencies.flush()
-    del frequencies
+    if rank == 0:
+        frequencies = np.memmap(freq_name, dtype=np.float32, shape=tuple(f32.shape), mode="w+")
+        frequencies[:] = f32.cpu().numpy()
+        frequencies.flush()
+        del frequencies
+    _barrier()
     frequencies = np.memmap(freq_name, dtype=np.float32, shape=tuple(f32.shape), mode="r+")
     return frequencies, freq_name
 
@@ -180,12 +257,15 @@ def compute_frequencies_memmap(genome, pattern, strand, workdir):
 def compute_frequencies_h5py(genome, pattern, strand, workdir):
     """HDF5 'frequencies_results' (dataset 'frequencies', float32) in a temp dir
     under workdir; returns (None, path) like the reference (:933-977)."""
-    folder = tempfile.mkdtemp(dir=workdir)
+    rank, _ = ranks()
+    folder = _shared_tempdir(workdir)
     res, n, dim = _profile_file(genome, pattern, strand, ("freq32",))
     if res is None:
         raise PhyloligoError("no FASTA record in {}".format(genome))
     freq_name = os.path.join(folder, "frequencies_results")
-    io_formats.write_hdf5(freq_name, "frequencies", res["freq32"].cpu().numpy())
+    if rank == 0:
+        io_formats.write_hdf5(freq_name, "frequencies", res["freq32"].cpu().numpy())
+    _barrier()
     return None, freq_name
 
 
@@ -215,46 +295,130 @@ def compute_frequencies(mthdrun, large, genome, pattern, strand, distchunksize, 
 # ---------------------------------------------------------------------------
 def compute_distances_device(frequencies, metric="Eucl"):
     """In-RAM float64 (N, N) matrix (the joblib/None and scoop conventions,
-    reference :313-392)."""
+    reference :313-392).  Under torchrun every rank computes its block rows and rank 0
+    receives them; the other ranks return None."""
     _check_metric(metric)
     device = engine.require_cuda()
     X = torch.from_numpy(np.ascontiguousarray(np.asarray(frequencies))).to(device)
-    return engine.distance_matrix_device(X, metric, torch.float64, symmetric=True).cpu().numpy()
+    rank, world = ranks()
+    if world == 1 or X.shape[0] < 2 * TILE * world:
+        res = engine.distance_matrix_device(X, metric, torch.float64, symmetric=True).cpu().numpy()
+        return res if rank == 0 else None
+    import torch.distributed as dist
+    from . import multigpu, sharding
+    n = int(X.shape[0])
+    P, aux, dim = engine.prepare(X, metric)
+    job = multigpu.BlockRows(n, torch.float64, rank, world)
+    job.compute(metric, P, aux, dim)
+    full = torch.empty((n, n), dtype=torch.float64, device=device) if rank == 0 else None
+    ops = []
+    for i, (a, b) in enumerate(job.ranges):
+        if b <= a:
+            continue
+        owner = sharding.range_owner(i, world)
+        if rank == 0 and owner == 0:
+            full[a:b].copy_(job.out_rows[i])
+        elif rank == 0:
+            ops.append(dist.P2POp(dist.irecv, full[a:b], owner))
+        elif owner == rank:
+            ops.append(dist.P2POp(dist.isend, job.out_rows[i], 0))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    res = full.cpu().numpy() if rank == 0 else None
+    job.close()
+    return res
 
 
-def _stream_to(sink_array, X, metric):
-    streamer = engine.PanelStreamer(X, _large_metric(metric), torch.float32, PANEL_ROWS)
+def _stream_rows(sink_array, X, metric):
+    """Fill the caller's (N, N) float32 array-like (memmap / HDF5 data region) with the matrix.
+    One GPU: row panels, upper triangle + mirror when the matrix fits in HBM.  Under torchrun:
+    every rank fills the rows it owns -- its paired block rows (upper triangle only, mirrored
+    tiles stored into the owner's rows over NVLink) when they fit in HBM, else plain row panels."""
+    rank, world = ranks()
+    metric = _large_metric(metric)
+    n = int(X.shape[0])
 
     def sink(r0, r1, host):
         sink_array[r0:r1] = host
 
-    streamer.run(sink)
+    if world == 1:
+        engine.PanelStreamer(X, metric, torch.float32, PANEL_ROWS).run(sink)
+        return
+    from . import multigpu, sharding
+    ranges = sharding.paired_row_ranges(n, world)
+    rows_owned = sum(ranges[i][1] - ranges[i][0] for i in sharding.owned_ranges(ranges, rank, world))
+    free, _ = torch.cuda.mem_get_info()
+    fits = torch.tensor([1 if rows_owned * n * 4 < 0.6 * free and n >= 2 * TILE * world else 0], device=X.device)
+    import torch.distributed as dist
+    dist.all_reduce(fits, op=dist.ReduceOp.MIN)  # every rank must take the same path
+    if int(fits.item()):
+        P, aux, dim = engine.prepare(X, metric)
+        job = multigpu.BlockRows(n, torch.float32, rank, world)
+        job.compute(metric, P, aux, dim)
+        pinned = [torch.empty((PANEL_ROWS, n), dtype=torch.float32).pin_memory() for _ in range(2)]
+        events, pending = [None, None], []
+        k = 0
+        for i in job.my_ranges:
+            a, b = job.ranges[i]
+            for r0 in range(a, b, PANEL_ROWS):
+                r1 = min(b, r0 + PANEL_ROWS)
+                slot = k & 1
+                while pending and pending[0][0] == slot:
+                    _, p0, p1 = pending.pop(0)
+                    events[slot].synchronize()
+                    sink(p0, p1, pinned[slot][:p1 - p0].numpy())
+                pinned[slot][:r1 - r0].copy_(job.out_rows[i][r0 - a:r1 - a], non_blocking=True)
+                events[slot] = torch.cuda.Event()
+                events[slot].record()
+                pending.append((slot, r0, r1))
+                k += 1
+        for slot, p0, p1 in pending:
+            events[slot].synchronize()
+            sink(p0, p1, pinned[slot][:p1 - p0].numpy())
+        job.close()
+    else:
+        for i in sharding.owned_ranges(ranges, rank, world):
+            a, b = ranges[i]
+            if b > a:
+                engine.PanelStreamer(X, metric, torch.float32, PANEL_ROWS, symmetric=False, rows=(a, b)).run(sink)
 
 
 def compute_distances_memmap(frequencies, freq_name, output, metric="Eucl"):
     """Raw row-major float32 N x N file at `output` (reference :394-427)."""
     _check_metric(metric)
     device = engine.require_cuda()
+    rank, _ = ranks()
     n = frequencies.shape[0]
-    distances = np.memmap(output, dtype=np.float32, shape=(n, n), mode="w+")
+    if rank == 0:
+        np.memmap(output, dtype=np.float32, shape=(n, n), mode="w+").flush()
+    _barrier()
+    distances = np.memmap(output, dtype=np.float32, shape=(n, n), mode="r+")
     X = torch.from_numpy(np.ascontiguousarray(np.asarray(frequencies))).to(device)
-    _stream_to(distances, X, metric)
+    _stream_rows(distances, X, metric)
     distances.flush()
     del distances
-    remove_folder(os.path.dirname(freq_name))
+    _barrier()
+    if rank == 0:
+        remove_folder(os.path.dirname(freq_name))
 
 
 def compute_distances_h5py(freq_name, dist_name, metric="Eucl"):
     """HDF5 file at `dist_name`, dataset 'distances' (N, N) float32 (reference :480-534)."""
     _check_metric(metric)
     device = engine.require_cuda()
+    rank, _ = ranks()
     freqs = io_formats.read_hdf5(freq_name, "frequencies")
     n = freqs.shape[0]
     X = torch.from_numpy(np.ascontiguousarray(freqs)).to(device)
-    with io_formats.Hdf5DatasetWriter(dist_name, "distances", (n, n), np.float32) as writer:
-        streamer = engine.PanelStreamer(X, _large_metric(metric), torch.float32, PANEL_ROWS)
-        streamer.run(lambda r0, r1, host: writer.write_rows(r0, host))
-    remove_folder(os.path.dirname(freq_name))
+    if rank == 0:
+        io_formats.Hdf5DatasetWriter(dist_name, "distances", (n, n), np.float32).close()
+    _barrier()
+    with io_formats.Hdf5DatasetWriter.attach(dist_name, "distances") as writer:
+        _stream_rows(writer.mm, X, metric)
+    _barrier()
+    if rank == 0:
+        remove_folder(os.path.dirname(freq_name))
 
 
 def compute_distances(mthdrun, large, frequencies, freq_name, out_file, dist, threads_max, freqchunksize, workdir):
@@ -317,11 +481,14 @@ def main(argv=None):
     if type(params.pattern) == int:  # -k given last: k-mer -> pattern without joker
         params.pattern = "1" * params.pattern
 
-    print("Using pattern {}".format(params.pattern))
-    if not os.path.isdir(params.workdir):
+    rank, world = ranks()
+    say = print if rank == 0 else (lambda *a, **k: None)
+    say("Using pattern {}".format(params.pattern))
+    if rank == 0 and not os.path.isdir(params.workdir):
         os.makedirs(params.workdir)
+    _barrier()
 
-    print("Computing frequencies")
+    say("Computing frequencies")
     frequencies, freq_name = compute_frequencies(params.mthdrun, params.large, params.genome, params.pattern,
                                                  params.strand, params.distchunksize, params.threads_max,
                                                  params.workdir)
@@ -333,17 +500,21 @@ def main(argv=None):
         else:
             freq_for_q = np.array(frequencies)
 
-    print("Computing Pairwise distances")
+    say("Computing Pairwise distances")
     res = compute_distances(params.mthdrun, params.large, frequencies, freq_name, params.out_file, params.dist,
                             params.threads_max, params.freqchunksize, params.workdir)
 
-    if params.out_freq_file:
-        print("Writing frequency matrix")
+    if params.out_freq_file and rank == 0:
+        say("Writing frequency matrix")
         io_formats.savetxt(params.out_freq_file, freq_for_q)
 
-    if not (params.mthdrun == "joblib" and params.large != "None"):
-        print("Writing distance matrix")
+    if not (params.mthdrun == "joblib" and params.large != "None") and rank == 0:
+        say("Writing distance matrix")
         io_formats.savetxt(params.out_file, res)
+    if world > 1:
+        import torch.distributed as dist
+        _barrier()
+        dist.destroy_process_group()
     return 0
 
 

@@ -122,3 +122,23 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("phylo_oracle", "oracle") or f == "_none_", (dirpath, f)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_savetxt_writes_the_bytes_numpy_writes(tmp_path, dtype):
+    """po_savetxt_host against np.savetxt(delimiter='\\t') -- the reference's writer, bin/phyloligo.py:1059-1066."""
+    rng = np.random.default_rng(0)
+    span = 300 if dtype == np.float64 else 30
+    A = (rng.standard_normal((211, 97)) * 10.0 ** rng.integers(-span, span, size=(211, 97))).astype(dtype)
+    A[0, 0], A[1, 1], A[2, 2], A[3, 3], A[4, 4] = np.nan, np.inf, -np.inf, 0.0, -0.0
+    A[5, 5] = np.finfo(dtype).tiny / 4  # subnormal
+    A[6, :] = rng.random(97)            # the range frequencies and distances live in
+    ours, ref = os.path.join(tmp_path, "a.txt"), os.path.join(tmp_path, "b.txt")
+    for threads in (0, 1, 3):
+        io_formats.savetxt(ours, A, threads=threads)
+        np.savetxt(ref, A, delimiter="\t")
+        assert open(ours, "rb").read() == open(ref, "rb").read()
+    for arr in (np.zeros((0, 5)), np.arange(7), np.zeros((3, 4), dtype=np.int64)):  # empty, 1-D, the all-zero int rows of :660
+        io_formats.savetxt(ours, arr)
+        np.savetxt(ref, arr, delimiter="\t")
+        assert open(ours, "rb").read() == open(ref, "rb").read()
