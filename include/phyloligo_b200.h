@@ -120,14 +120,18 @@ int po_profile_batch(const uint8_t* d_text, const int64_t* d_begin, const int64_
  *   EuclGram  : centred float16 hi/lo operand blocks for the tensor-core kernel (n rounded up to
  *               128, dim to 64, 4 bytes per element), float64 column sums, and a float32 copy of
  *               the profiles for the exact recomputation of cancelling entries
- *   SC        : the same count of int32 (centred doubled average ranks)
+ *   SC        : 64 <= dim <= 4096: the centred doubled average ranks 2 rank - (dim+1) as two float16
+ *               integer digits (r = 64 hi + lo) in the EuclGram block layout (n rounded up to 128,
+ *               dim to 64, 4 bytes per element) -- Spearman runs on the tensor cores, exactly;
+ *               otherwise n rows of dim (rounded up to 4) int32 ranks for the CUDA-core kernel
  *   KT        : n rows of packed order-relation bit masks, 2 * ceil(dim(dim-1)/2 / 128) * 16 bytes
  *   JSD       : float32 with exact zeros biased to 1e-30, dim rounded up to a multiple of 32
  *               and n to a multiple of 64, stored as bulk-copy blocks: [n/64][dim/32] blocks
  *               of [32 dims][64 profiles], then [n/32][dim/32] blocks of
  *               [32 dims][32 profiles][2] (every value twice, for packed f32x2 math)
- * po_prepared_row_bytes is the per-profile figure (exact for every metric but JSD,
- * whose buffer is padded to whole groups of 64 profiles).
+ * po_prepared_row_bytes is the per-profile figure of the row-major layouts (Eucl, BC, KT, and
+ * the CUDA-core SC layout); the blocked layouts (JSD, EuclGram, tensor-core SC) are padded to
+ * whole groups of profiles -- use po_prepared_bytes.
  */
 int64_t po_prepared_bytes(int metric, int64_t n, int64_t dim);
 int64_t po_prepared_row_bytes(int metric, int64_t dim);

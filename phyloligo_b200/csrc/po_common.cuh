@@ -74,7 +74,11 @@ bool eucl_use_gram(int metric, int64_t dim);
 int64_t gram_prepared_bytes(int64_t n, int64_t dim);
 int launch_gram_prepare(const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx, void* d_P, double* d_aux,
                         cudaStream_t stream);
-int launch_gram(const void* d_P, const double* d_aux, int64_t n, int64_t dim, int64_t row0, int64_t row1, int64_t col0,
+bool sc_use_gram(int metric, int64_t dim);
+int64_t sc_gram_prepared_bytes(int64_t n, int64_t dim);
+int launch_sc_gram_prepare(const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx, void* d_P, double* d_aux,
+                           cudaStream_t stream);
+int launch_gram(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim, int64_t row0, int64_t row1, int64_t col0,
                 int64_t col1, void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0, void* d_mir,
                 int64_t ld_mir, int64_t mir_row0, int64_t mir_col0, int out_dtype, unsigned flags, cudaStream_t stream);
 

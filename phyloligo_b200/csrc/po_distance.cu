@@ -301,8 +301,8 @@ int launch_distance(int metric, const void* d_P, const double* d_aux, int64_t n,
                     void* d_mir, int64_t ld_mir, int64_t mir_row0, int64_t mir_col0,
                     int out_dtype, unsigned flags, cudaStream_t stream) {
     if (row1 <= row0 || col1 <= col0) return PO_OK;
-    if (eucl_use_gram(metric, dim))
-        return launch_gram(d_P, d_aux, n, dim, row0, row1, col0, col1, d_out, ld_out, out_row0, out_col0, d_mir, ld_mir,
+    if (eucl_use_gram(metric, dim) || sc_use_gram(metric, dim))
+        return launch_gram(metric, d_P, d_aux, n, dim, row0, row1, col0, col1, d_out, ld_out, out_row0, out_col0, d_mir, ld_mir,
                            mir_row0, mir_col0, out_dtype, flags, stream);
     TileParams p;
     p.P = reinterpret_cast<const uint32_t*>(d_P);

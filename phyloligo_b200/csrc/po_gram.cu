@@ -34,6 +34,7 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "po_common.cuh"
+#include "po_rank.cuh"
 
 namespace po {
 
@@ -42,7 +43,7 @@ constexpr int GK = 64;                  // K elements per block (4 MMAs of K = 1
 constexpr int GBLOCK_BYTES = GT * GK * 2;     // one operand block: 16 KB
 constexpr int GSTAGE_BYTES = 4 * GBLOCK_BYTES;  // A hi, A lo, B hi, B lo
 constexpr int GSTAGES = 3;
-constexpr int GTHREADS = 128;
+constexpr int GTHREADS = 512;             // 16 warps: two of them also drive the pipeline, all 16 share the epilogue
 constexpr int GRASTER = 16;             // tile columns per rasterisation chunk
 constexpr float GSCALE = 16384.0f;      // 2^14
 constexpr double GUNSCALE = 1.0 / (16384.0 * 16384.0);
@@ -62,6 +63,25 @@ int64_t gram_prepared_bytes(int64_t n, int64_t dim) {
     const int64_t npad = (n + GT - 1) / GT * GT;
     const int64_t ldk = gram_ldk(dim);
     return npad * ldk * 4 + ldk * 8 + n * ldk * 4 + (int64_t)GSUM_SLICES * ldk * 8;
+}
+
+// Spearman on the same kernel.  1 - rho is a Gram form as well: with r' = 2 rank - (dim + 1) (integer,
+// centred; average ranks for ties -- the scipy.stats.spearmanr step of phylodist.SC, reference
+// core/phylodist.py:82-85), rho = r'_a . r'_b / sqrt(|r'_a|^2 |r'_b|^2).  r' is split into two
+// integer digits r' = 64 h + l, l in [-32, 31], both exact in float16; the tensor cores form
+// h.h', (h.l' + l.h') and l.l' in the three TMEM accumulators.  Every product and every partial sum
+// is an integer below 2^24 for dim <= 4096, so the float32 accumulators are exact and the epilogue
+// rebuilds the integer dot product 4096 hh + 64 x + ll: the result is bit for bit that of the
+// CUDA-core kernel (po_distance.cu, K_SC).  PO_SC_CUDA_CORES=1 selects that kernel instead.
+bool sc_use_gram(int metric, int64_t dim) {
+    if (metric != PO_SC) return false;
+    const char* e = getenv("PO_SC_CUDA_CORES");
+    if (e && e[0] == '1') return false;
+    return dim >= 64 && dim <= 4096;
+}
+int64_t sc_gram_prepared_bytes(int64_t n, int64_t dim) {
+    const int64_t npad = (n + GT - 1) / GT * GT;
+    return npad * gram_ldk(dim) * 4;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -175,6 +195,59 @@ int launch_gram_prepare(const void* d_X, int dtype, int64_t n, int64_t dim, int6
     return launch_gram_prepare_t<double>(d_X, n, dim, ldx, d_P, d_aux, stream);
 }
 
+// SC operands: one CTA per profile ranks it (O(dim^2) comparisons out of shared memory, as
+// prepare_rank_kernel of po_prepare.cu) and scatters the two float16 digits of every centred doubled
+// rank into the hi / lo operand blocks.  The block region is zeroed first (padding rows and dimensions).
+template <typename T>
+__global__ void __launch_bounds__(256) sc_blocks_kernel(const T* __restrict__ X, int64_t n, int64_t dim, int64_t ldx,
+                                                        unsigned char* __restrict__ P, int nkb, int dpad,
+                                                        double* __restrict__ aux) {
+    extern __shared__ __align__(8) unsigned char g_rank_smem[];
+    __shared__ unsigned long long s_ss;
+    const int64_t row = blockIdx.x;
+    if (threadIdx.x == 0) s_ss = 0ull;
+    const int64_t grp = row / GT;
+    const int rr = (int)(row % GT);
+    unsigned long long ss = rank_transform_row<T>(X + row * ldx, (int)dim, dpad, g_rank_smem, [&](int e, int val) {
+        const int lo = ((val + 32) & 63) - 32;     // [-32, 31]
+        const int hi = (val - lo) / 64;            // exact
+        const int kb = e / GK, kk = e % GK;
+        unsigned char* blk_hi = P + ((size_t)grp * nkb + kb) * 2 * GBLOCK_BYTES;
+        const size_t off = ((size_t)(kk >> 3) * 16 + (rr >> 3)) * 128 + (rr & 7) * 16 + (kk & 7) * 2;
+        *reinterpret_cast<__half*>(blk_hi + off) = __int2half_rn(hi);
+        *reinterpret_cast<__half*>(blk_hi + GBLOCK_BYTES + off) = __int2half_rn(lo);
+    });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+    if ((threadIdx.x & 31) == 0 && ss) atomicAdd(&s_ss, ss);
+    __syncthreads();
+    if (threadIdx.x == 0) aux[row] = (double)s_ss;
+}
+
+int launch_sc_gram_prepare(const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx, void* d_P, double* d_aux,
+                           cudaStream_t stream) {
+    if (!d_aux) {
+        set_error("SC needs d_aux");
+        return PO_ERR_ARG;
+    }
+    const int nkb = (int)(gram_ldk(dim) / GK);
+    PO_CUDA_CHECK(cudaMemsetAsync(d_P, 0, (size_t)sc_gram_prepared_bytes(n, dim), stream));
+    const size_t sm = rank_smem_bytes(dim);
+    const int dpad = (int)rank_pad(dim);
+    if (dtype == PO_F32) {
+        PO_CUDA_CHECK(cudaFuncSetAttribute(sc_blocks_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        sc_blocks_kernel<float><<<(unsigned)n, 256, sm, stream>>>(reinterpret_cast<const float*>(d_X), n, dim, ldx,
+                                                                  reinterpret_cast<unsigned char*>(d_P), nkb, dpad, d_aux);
+    } else {
+        PO_CUDA_CHECK(cudaFuncSetAttribute(sc_blocks_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        sc_blocks_kernel<double><<<(unsigned)n, 256, sm, stream>>>(reinterpret_cast<const double*>(d_X), n, dim, ldx,
+                                                                   reinterpret_cast<unsigned char*>(d_P), nkb, dpad, d_aux);
+    }
+    count_launch(2);
+    PO_LAUNCH_CHECK("sc_blocks_kernel");
+    return PO_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // tile kernel
 // ---------------------------------------------------------------------------------------------
@@ -254,11 +327,14 @@ struct GramParams {
     unsigned flags;
 };
 
-template <typename OUT_T>
+enum GramMode { GM_EUCL = 0, GM_SC = 1 };
+
+template <typename OUT_T, int MODE>
 __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams p) {
     extern __shared__ __align__(1024) unsigned char gsmem[];
     __shared__ __align__(8) unsigned long long bars[2 * GSTAGES + 1];
     __shared__ uint32_t s_tmem;
+    __shared__ double s_nb[GT];  // the tile columns' row constants (squared norms / rank sums)
     // rasterisation: chunks of GRASTER tile columns, all tile rows inside a chunk, so that the
     // chunk's column operands (GRASTER x 2 MB at 4096 dimensions) stay in L2 while the rows stream
     const int64_t per_chunk = p.tiles_r * GRASTER;
@@ -322,8 +398,14 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
                 const uint64_t dbh = g_smem_desc(b_hi + koff), dbl = g_smem_desc(b_lo + koff);
                 const unsigned acc = (kb > 0 || ks > 0) ? 1u : 0u;
                 g_mma_f16(tmem, dah, dbh, idesc, acc);
-                g_mma_f16(tmem + GT, dah, dbl, idesc, acc);
-                g_mma_f16(tmem + 2 * GT, dal, dbh, idesc, acc);
+                if (MODE == GM_EUCL) {
+                    g_mma_f16(tmem + GT, dah, dbl, idesc, acc);
+                    g_mma_f16(tmem + 2 * GT, dal, dbh, idesc, acc);
+                } else {  // integer digits: the cross terms share an accumulator, lo.lo is kept
+                    g_mma_f16(tmem + GT, dah, dbl, idesc, acc);
+                    g_mma_f16(tmem + GT, dal, dbh, idesc, 1u);
+                    g_mma_f16(tmem + 2 * GT, dal, dbl, idesc, acc);
+                }
             }
             g_mma_commit(empty0 + 8 * s);  // the stage is free once these MMAs have read it
         }
@@ -331,10 +413,20 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
     }
     __syncwarp();
 
-    // ===== epilogue: one accumulator row per thread =====
+    // ===== epilogue: warp w owns TMEM lanes 32 (w & 3) .. +31 (the rows a warp may read) and the
+    // 32 columns 32 (w >> 2) .. +31, in two chunks of 16.  Mirrored entries are stored straight from
+    // the registers (lanes = consecutive rows = consecutive addresses of the mirrored row); the
+    // direct entries go through a 32 x 33 shared-memory transpose so that a warp stores 128
+    // contiguous bytes of one output row per instruction.  The operand ring is free by now.
+    const int lq = warp & 3, cq = warp >> 2;
+    if (tid < GT) {
+        const int64_t gc = col_base + tid;
+        s_nb[tid] = (gc < p.n) ? p.aux[gc] : 0.0;
+    }
+    __syncthreads();
     g_mbar_wait(accum, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int r = warp * 32 + lane;  // tile row == TMEM lane
+    const int r = lq * 32 + lane;  // tile row == TMEM lane
     const int64_t grow = row_base + r;
     const bool row_ok = grow >= p.row0 && grow < p.row1;
     const double na = (grow < p.n) ? p.aux[grow] : 0.0;
@@ -342,10 +434,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
     OUT_T* mir = reinterpret_cast<OUT_T*>(p.mir);
     const bool do_mirror = (p.flags & PO_FLAG_MIRROR) && row_base + GT <= col_base;
     const int64_t ldx32 = (int64_t)nkb * GK;
+    OUT_T* tbuf = reinterpret_cast<OUT_T*>(gsmem) + (size_t)warp * (32 * 33);
 #pragma unroll 1
-    for (int c0 = 0; c0 < GT; c0 += 16) {
+    for (int half = 0; half < 2; ++half) {
+        const int c0 = cq * 32 + half * 16;
         uint32_t vh[16], vx[16], vy[16];
-        const unsigned ta = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
+        const unsigned ta = tmem + ((unsigned)(lq * 32) << 16) + (unsigned)c0;
         g_tmem_ld16(ta, vh);
         g_tmem_ld16(ta + GT, vx);
         g_tmem_ld16(ta + 2 * GT, vy);
@@ -355,7 +449,17 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int64_t gcol = col_base + c0 + j;
-            const double nb = (gcol < p.n) ? p.aux[gcol] : 0.0;
+            const double nb = s_nb[c0 + j];
+            if (MODE == GM_SC) {
+                // exact integer dot product of the centred doubled ranks, then 1 - rho as K_SC does
+                const long long t = 4096ll * (long long)__uint_as_float(vh[j]) + 64ll * (long long)__uint_as_float(vx[j]) +
+                                    (long long)__uint_as_float(vy[j]);
+                const double den = sqrt(na * nb);
+                const double v = (den == 0.0) ? __longlong_as_double(0x7FF8000000000000ll)  // scipy: NaN for a constant row
+                                              : 1.0 - (double)t / den;
+                val[j] = (OUT_T)v;
+                continue;
+            }
             const float dot = __uint_as_float(vh[j]) + (__uint_as_float(vx[j]) + __uint_as_float(vy[j]));
             double d2 = na + nb - 2.0 * (double)dot;
             const bool inside = row_ok && gcol >= p.col0 && gcol < p.col1;
@@ -366,12 +470,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
             if (grow == gcol) val[j] = (OUT_T)0;  // sklearn forces an exact zero diagonal
         }
         // exact recomputation, one entry at a time, by the whole warp
-        unsigned lanes = __ballot_sync(0xFFFFFFFFu, cancel != 0u);
+        unsigned lanes = (MODE == GM_EUCL) ? __ballot_sync(0xFFFFFFFFu, cancel != 0u) : 0u;
         while (lanes) {
             const int l = __ffs(lanes) - 1;
             lanes &= lanes - 1;
             unsigned m = __shfl_sync(0xFFFFFFFFu, cancel, l);
-            const int64_t er = row_base + warp * 32 + l;
+            const int64_t er = row_base + lq * 32 + l;
             while (m) {
                 const int j = __ffs(m) - 1;
                 m &= m - 1;
@@ -399,10 +503,20 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int64_t gcol = col_base + c0 + j;
-            if (row_ok && gcol >= p.col0 && gcol < p.col1) {
-                out[(grow - p.out_row0) * p.ld_out + (gcol - p.out_col0)] = val[j];
-                if (do_mirror) mir[(gcol - p.mir_row0) * p.ld_mir + (grow - p.mir_col0)] = val[j];
-            }
+            if (do_mirror && row_ok && gcol >= p.col0 && gcol < p.col1)
+                mir[(gcol - p.mir_row0) * p.ld_mir + (grow - p.mir_col0)] = val[j];
+            tbuf[lane * 33 + half * 16 + j] = val[j];
+        }
+    }
+    __syncwarp();
+    {
+        const int64_t gcol = col_base + cq * 32 + lane;
+        const bool col_ok = gcol >= p.col0 && gcol < p.col1;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+            const int64_t gr = row_base + lq * 32 + rr;
+            if (col_ok && gr >= p.row0 && gr < p.row1)
+                out[(gr - p.out_row0) * p.ld_out + (gcol - p.out_col0)] = tbuf[rr * 33 + lane];
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -410,11 +524,18 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }
 
-int launch_gram(const void* d_P, const double* d_aux, int64_t n, int64_t dim, int64_t row0, int64_t row1, int64_t col0,
-                int64_t col1, void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0, void* d_mir,
+template <typename OUT_T, int MODE>
+static int launch_gram_t(const GramParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+    PO_CUDA_CHECK(cudaFuncSetAttribute(gram_tile_kernel<OUT_T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gram_tile_kernel<OUT_T, MODE><<<grid, GTHREADS, smem, stream>>>(p);
+    return PO_OK;
+}
+
+int launch_gram(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim, int64_t row0, int64_t row1,
+                int64_t col0, int64_t col1, void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0, void* d_mir,
                 int64_t ld_mir, int64_t mir_row0, int64_t mir_col0, int out_dtype, unsigned flags, cudaStream_t stream) {
     if (!d_aux) {
-        set_error("Eucl (tensor-core path) needs d_aux from po_prepare_profiles");
+        set_error("the tensor-core path needs d_aux from po_prepare_profiles");
         return PO_ERR_ARG;
     }
     GramParams p;
@@ -442,13 +563,14 @@ int launch_gram(const void* d_P, const double* d_aux, int64_t n, int64_t dim, in
     const size_t smem = (size_t)GSTAGES * GSTAGE_BYTES + 1024;
     dim3 grid((unsigned)(tr * tc), 1, 1);
     LaunchTimer tm(1, stream);
-    if (out_dtype == PO_F32) {
-        PO_CUDA_CHECK(cudaFuncSetAttribute(gram_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gram_tile_kernel<float><<<grid, GTHREADS, smem, stream>>>(p);
-    } else {
-        PO_CUDA_CHECK(cudaFuncSetAttribute(gram_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gram_tile_kernel<double><<<grid, GTHREADS, smem, stream>>>(p);
-    }
+    int rc;
+    if (metric == PO_SC)
+        rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_SC>(p, grid, smem, stream)
+                                 : launch_gram_t<double, GM_SC>(p, grid, smem, stream);
+    else
+        rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_EUCL>(p, grid, smem, stream)
+                                 : launch_gram_t<double, GM_EUCL>(p, grid, smem, stream);
+    if (rc != PO_OK) return rc;
     count_launch(1);
     PO_LAUNCH_CHECK("gram_tile_kernel");
     return PO_OK;

@@ -23,6 +23,7 @@
 //                interleaved in groups of 4 up-words then 4 down-words so the tile
 //                kernel reads them with 128-bit loads.  aux = number of untied pairs.
 #include "po_common.cuh"
+#include "po_rank.cuh"
 
 namespace po {
 
@@ -43,6 +44,7 @@ int64_t prepared_bytes(int metric, int64_t n, int64_t dim) {
     const int64_t ldp = prepared_row_elems(metric, dim);
     if (metric == PO_JSD) return 3 * ((n + 63) / 64 * 64) * ldp * 4;  // blocked B + doubled A, rows padded to 64
     if (eucl_use_gram(metric, dim)) return gram_prepared_bytes(n, dim);
+    if (sc_use_gram(metric, dim)) return sc_gram_prepared_bytes(n, dim);
     return n * ldp * 4;
 }
 
@@ -117,33 +119,18 @@ __global__ void __launch_bounds__(256) prepare_jsd_kernel(const void* __restrict
     }
 }
 
-// SC: centred doubled average ranks, O(dim^2) comparisons per row out of shared memory.
+// SC: centred doubled average ranks (po_rank.cuh: shared-memory sort + tie groups).
 template <typename T>
 __global__ void __launch_bounds__(256) prepare_rank_kernel(const void* __restrict__ X, int64_t n, int64_t dim,
-                                                           int64_t ldx, int* __restrict__ P, int64_t ldp,
+                                                           int64_t ldx, int* __restrict__ P, int64_t ldp, int dpad,
                                                            double* __restrict__ aux) {
-    extern __shared__ double srow[];
+    extern __shared__ __align__(8) unsigned char rank_smem[];
     __shared__ unsigned long long s_ss;
     const int64_t row = blockIdx.x;
-    for (int64_t e = threadIdx.x; e < dim; e += blockDim.x) srow[e] = load_as_double<T>(X, row * ldx + e);
     if (threadIdx.x == 0) s_ss = 0ull;
-    __syncthreads();
-    unsigned long long ss = 0ull;
-    for (int64_t e = threadIdx.x; e < ldp; e += blockDim.x) {
-        int val = 0;
-        if (e < dim) {
-            const double v = srow[e];
-            int less = 0, eq = 0;
-            for (int64_t j = 0; j < dim; ++j) {
-                const double w = srow[j];
-                less += (w < v);
-                eq += (w == v);
-            }
-            val = 2 * less + eq - (int)dim;
-            ss += (unsigned long long)((long long)val * (long long)val);
-        }
-        P[row * ldp + e] = val;
-    }
+    for (int64_t e = dim + threadIdx.x; e < ldp; e += blockDim.x) P[row * ldp + e] = 0;  // padding
+    unsigned long long ss = rank_transform_row<T>(reinterpret_cast<const T*>(X) + row * ldx, (int)dim, dpad, rank_smem,
+                                                  [&](int e, int val) { P[row * ldp + e] = val; });
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
     if ((threadIdx.x & 31) == 0 && ss) atomicAdd(&s_ss, ss);
@@ -230,15 +217,15 @@ static int launch_prepare_t(int metric, const void* d_X, int64_t n, int64_t dim,
                 set_error("SC needs d_aux");
                 return PO_ERR_ARG;
             }
-            const size_t sm = (size_t)dim * sizeof(double);
+            const size_t sm = rank_smem_bytes(dim);
             auto kern = prepare_rank_kernel<T>;
             if (sm > 200 * 1024) {
                 set_error("SC: profile dimension %lld too large for the rank kernel", (long long)dim);
                 return PO_ERR_UNSUPPORTED;
             }
-            if (sm > 48 * 1024)
+            if (sm > 32 * 1024)  // static + dynamic shared memory beyond the 48 KB default needs the opt-in
                 PO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            kern<<<grid, 256, sm, stream>>>(d_X, n, dim, ldx, (int*)d_P, ldp, d_aux);
+            kern<<<grid, 256, sm, stream>>>(d_X, n, dim, ldx, (int*)d_P, ldp, (int)rank_pad(dim), d_aux);
             count_launch(2);
             PO_LAUNCH_CHECK("prepare_rank_kernel");
             return PO_OK;
@@ -271,6 +258,13 @@ int launch_prepare(int metric, const void* d_X, int dtype, int64_t n, int64_t di
     if (n == 0) return PO_OK;
     if (eucl_use_gram(metric, dim) && (dtype == PO_F32 || dtype == PO_F64))
         return launch_gram_prepare(d_X, dtype, n, dim, ldx, d_P, d_aux, stream);
+    if (sc_use_gram(metric, dim) && (dtype == PO_F32 || dtype == PO_F64)) {
+        if (n > 0x7FFFFFFFll) {
+            set_error("too many rows (%lld)", (long long)n);
+            return PO_ERR_UNSUPPORTED;
+        }
+        return launch_sc_gram_prepare(d_X, dtype, n, dim, ldx, d_P, d_aux, stream);
+    }
     if (n > 0x7FFFFFFFll) {
         set_error("too many rows (%lld)", (long long)n);
         return PO_ERR_UNSUPPORTED;

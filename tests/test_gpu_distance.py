@@ -205,3 +205,30 @@ def test_tensor_core_euclidean(n, dim):
     engine.distance_block("EuclGram", P, aux, d, 70, 110, 0, n, blk, 70, 0)
     # the float32 epilogue takes a float32 square root of the same float64 d^2
     assert np.allclose(blk.cpu().numpy(), got[70:110], rtol=2e-7, atol=0)
+
+
+@pytest.mark.parametrize("n,dim", [(130, 64), (300, 256), (129, 1024), (140, 4096), (70, 200)])
+def test_tensor_core_spearman_is_exact(n, dim, monkeypatch):
+    """SC on tcgen05 (integer float16 digit planes, exact float32 accumulation): bit for bit the
+    CUDA-core integer kernel, 1e-12 from scipy.stats.spearmanr, NaN for constant rows."""
+    rng = np.random.default_rng(dim * 7 + n)
+    X = rng.integers(0, 12, size=(n, dim)).astype(np.float64)  # tie-heavy
+    X[: n // 2] = rng.random((n // 2, dim))                     # and tie-free rows (largest rank sums)
+    X[3] = 0.0                                                  # constant row -> NaN
+    X[5] = np.arange(dim)                                       # extreme ranks: +/-(dim-1)
+    X[6] = -np.arange(dim)
+    X /= np.maximum(X.sum(axis=1, keepdims=True), 1e-300)
+    for dtype in (torch.float64, torch.float32):
+        monkeypatch.setenv("PO_SC_CUDA_CORES", "1")
+        ref = _gpu_matrix(X, "SC", dtype, symmetric=True)
+        monkeypatch.delenv("PO_SC_CUDA_CORES")
+        got = _gpu_matrix(X, "SC", dtype, symmetric=True)
+        full = _gpu_matrix(X, "SC", dtype, symmetric=False)
+        assert np.array_equal(got, ref, equal_nan=True)
+        assert np.array_equal(full, ref, equal_nan=True)
+    want = np.array([[po.SC(a, b) for b in X[:24]] for a in X[:24]])
+    sub = _gpu_matrix(X, "SC", torch.float64, symmetric=True)[:24, :24]
+    assert np.array_equal(np.isnan(sub), np.isnan(want))
+    m = ~np.isnan(want)
+    assert np.abs(sub[m] - want[m]).max() < 1e-12
+    assert sub[5, 6] == 2.0 and sub[5, 5] == 0.0
