@@ -198,7 +198,7 @@ def run_reference(args):
     n_contigs = max(64, int(round(100_000 * args.scale)))
     total_bases = n_contigs * args.mean_len
     cores = os.cpu_count() or 1
-    n_profile = min(n_contigs, max(16, 2 * cores))
+    n_profile = min(n_contigs, max(64, 8 * cores))  # a few seconds of work per step on all cores
     n_dist = min(n_contigs, 400)
     seqs = sample_sequences(max(n_profile, n_dist), args.mean_len)
     vals, detail = [], None
@@ -511,18 +511,19 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            seqs = sample_sequences(300, args.mean_len)
-            spb, spp, d1 = cpu_python_port_rates(seqs, 60, 300, 1)
+            # about 10-15 s of single-core CPU work: 300 contigs profiled (~1 us per base), 700 profiles all-pairs
+            seqs = sample_sequences(700, args.mean_len)
+            spb, spp, d1 = cpu_python_port_rates(seqs, 300, 700, 1)
             cval = whole_job_pairs_per_s(n_contigs, total_bases, spb, spp)
-            cspb, cspp, d2 = cpu_c_port_rates(seqs, 300, 300, cores)
+            cspb, cspp, d2 = cpu_c_port_rates(seqs, 700, 700, cores)
             line["cpu_baseline"] = {
                 "value": cval, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": "Python port of the reference path on 1 core: 60 contigs profiled (%.1f s), 300 profiles "
+                "sample": "Python port of the reference path on 1 core: %d contigs profiled (%.1f s), %d profiles "
                           "all-pairs JSD (%.1f s); value = whole-job pairs/s those rates imply for this workload"
-                          % (d1["profile_s"], d1["dist_s"]),
+                          % (d1["profile_contigs"], d1["profile_s"], d1["dist_rows"], d1["dist_s"]),
                 "seconds_per_base": spb, "seconds_per_pair": spp,
                 "c_port": {"value": whole_job_pairs_per_s(n_contigs, total_bases, cspb, cspp), "unit": UNIT,
-                           "cores": cores, "note": "multi-threaded C restatement (oracle/oracle.c), same sample sizes x5"},
+                           "cores": cores, "note": "multi-threaded C restatement (oracle/oracle.c): 700 contigs profiled, 700 profiles all-pairs"},
             }
         emit(line)
     if world > 1:
