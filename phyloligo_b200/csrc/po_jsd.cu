@@ -27,10 +27,12 @@
 //
 // Two-phase evaluation.  Phase 1 adds the series value q*G(u) for every term and tracks
 // the largest u it met.  If some lane of the warp met u > 1/2 in this dimension, phase 2
-// forms the log-based value of all 16 terms (packed, branch free) and adds the difference
-// to the series value for exactly those with u > 1/2 (G's polynomial is finite on [0, 1],
-// so the provisional value is harmless).  The result of a pair depends only on that
-// pair's data.  Dense profiles (4^k bins well covered) rarely need phase 2; sparse ones
+// walks the 8 packed term pairs and, for those in which some lane has u > 1/2 (a
+// warp-uniform test: typically the pairs of one outlier profile of the tile), forms the
+// log-based value and adds the difference to the series value for exactly the terms with
+// u > 1/2 (G's polynomial is finite on [0, 1], so the provisional value is harmless).
+// The result of a pair depends only on that pair's data.  Dense profiles (4^k bins well
+// covered) need phase 2 in a few percent of the (warp, dimension) steps; sparse ones
 // (5 kb contigs at k = 5) need it almost always and run about 1.6x slower per term.
 #include "po_common.cuh"
 
@@ -49,6 +51,9 @@ constexpr int JDK = 32;            // dimensions per chunk
 #endif
 #ifndef JSD_CTAS
 #define JSD_CTAS 4
+#endif
+#ifndef JSD_BLOCK_P2
+#define JSD_BLOCK_P2 1  // phase 2 only for the term pairs that need it
 #endif
 constexpr int JSTAGES = JSD_STAGES;
 constexpr int JUNROLL = JSD_UNROLL;
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdP
             const ulonglong2 A01 = sA[d * 16], A23 = sA[d * 16 + 1], Bv = sB[d * 16];
             const u64 a2[4] = {A01.x, A01.y, A23.x, A23.y};
             const u64 b2[2] = {Bv.x, Bv.y};
-            u64 dd[4][2], xx[4][2], uu[4][2], rr[4][2];
+            u64 dd[4][2], xx[4][2], uu[4][2];
             float umax = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -246,35 +251,43 @@ __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdP
                     dd[i][j] = sub2(a2[i], b2[j]);
                     float s0, s1;
                     upk2(sm, s0, s1);
-                    rr[i][j] = pk2(rcp_approx(s0), rcp_approx(s1));
-                    xx[i][j] = mul2(dd[i][j], rr[i][j]);
+                    xx[i][j] = mul2(dd[i][j], pk2(rcp_approx(s0), rcp_approx(s1)));
                     uu[i][j] = mul2(xx[i][j], xx[i][j]);
                     float u0, u1;
                     upk2(uu[i][j], u0, u1);
                     umax = fmaxf(umax, fmaxf(u0, u1));
                 }
+            // largest u of the warp's 512 terms in this dimension (decides phase 2 below).  Choosing a
+            // lower-degree fit of G per (warp, dimension) from it was tried and measured slower: the extra
+            // warp-uniform branch splits the MUFU / FMA interleave of consecutive dimensions.
+            const unsigned umax_w = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(umax));  // u >= 0: bit order = value order
             u64 G[4][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) G[i][j] = fma2(g6, uu[i][j], g5);
-#define JSD_HORNER(gk)                          \
+#define JSD_HORNER_FIRST(ga, gb)                  \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) \
+        _Pragma("unroll") for (int j = 0; j < 2; ++j) G[i][j] = fma2(ga, uu[i][j], gb);
+#define JSD_HORNER(gk)                            \
     _Pragma("unroll") for (int i = 0; i < 4; ++i) \
         _Pragma("unroll") for (int j = 0; j < 2; ++j) G[i][j] = fma2(G[i][j], uu[i][j], gk);
-            JSD_HORNER(g4)
-            JSD_HORNER(g3)
-            JSD_HORNER(g2)
-            JSD_HORNER(g1)
-            JSD_HORNER(g0)
+            {
+                JSD_HORNER_FIRST(g6, g5)
+                JSD_HORNER(g4)
+                JSD_HORNER(g3)
+                JSD_HORNER(g2)
+                JSD_HORNER(g1)
+                JSD_HORNER(g0)
+            }
 #undef JSD_HORNER
+#undef JSD_HORNER_FIRST
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) c2[i][j] = fma2(mul2(dd[i][j], xx[i][j]), G[i][j], c2[i][j]);
 
-            if (__any_sync(0xFFFFFFFFu, umax > 0.5f)) {
-                // phase 2, branch free and packed: for every term form the log-based value
-                // s * fB(min(a,b)/s) and add (that - series value) where u > 1/2, 0 elsewhere
+            if (umax_w > 0x3F000000u /* 0.5f */) {
+                // phase 2, packed: for the term pairs in which some lane met u > 1/2, form the log-based
+                // value s * fB(min(a,b)/s) and add (that - series value) where u > 1/2, 0 elsewhere.
+                // Typically a few of the 8 pairs are concerned (one outlier profile of the tile); sparse
+                // profiles flag all of them.
                 float a[4], b[4], dummy;
                 upk2(a2[0], a[0], dummy);
                 upk2(a2[1], a[1], dummy);
@@ -289,7 +302,16 @@ __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdP
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        const u64 v = mul2(pk2(fminf(a[i], b[2 * j]), fminf(a[i], b[2 * j + 1])), rr[i][j]);
+                        float u0, u1;
+                        upk2(uu[i][j], u0, u1);
+#if JSD_BLOCK_P2
+                        if (!__any_sync(0xFFFFFFFFu, (u0 > 0.5f) | (u1 > 0.5f))) continue;
+#endif
+                        const u64 sm = add2(a2[i], b2[j]);
+                        float s0, s1;
+                        upk2(sm, s0, s1);  // 1/s again (same MUFU result as in phase 1) rather than 16 live registers
+                        const u64 v = mul2(pk2(fminf(a[i], b[2 * j]), fminf(a[i], b[2 * j + 1])),
+                                           pk2(rcp_approx(s0), rcp_approx(s1)));
                         u64 E = fma2(e4, v, e3);
                         E = fma2(E, v, e2);
                         E = fma2(E, v, e1);
@@ -297,12 +319,10 @@ __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdP
                         float v0, v1;
                         upk2(v, v0, v1);
                         const u64 fB = fma2(mul2(v, ln4), pk2(lg2_approx(v0), lg2_approx(v1)), E);
-                        const u64 sm = add2(a2[i], b2[j]);
                         const u64 series = mul2(mul2(dd[i][j], xx[i][j]), G[i][j]);
                         const u64 delta = sub2(mul2(sm, fB), series);
-                        float d0, d1, u0, u1;
+                        float d0, d1;
                         upk2(delta, d0, d1);
-                        upk2(uu[i][j], u0, u1);
                         c2[i][j] = add2(c2[i][j], pk2(u0 > 0.5f ? d0 : 0.f, u1 > 0.5f ? d1 : 0.f));
                     }
             }
