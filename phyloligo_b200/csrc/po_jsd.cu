@@ -52,6 +52,9 @@ constexpr int JDK = 32;            // dimensions per chunk
 #ifndef JSD_CTAS
 #define JSD_CTAS 4
 #endif
+#ifndef JSD_P2_BITS
+#define JSD_P2_BITS 0x3F000000u  // 0.5f: a warp that met a larger u in a dimension runs phase 2 for it
+#endif
 #ifndef JSD_BLOCK_P2
 #define JSD_BLOCK_P2 1  // phase 2 only for the term pairs that need it
 #endif
@@ -283,7 +286,8 @@ __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdP
 #pragma unroll
                 for (int j = 0; j < 2; ++j) c2[i][j] = fma2(mul2(dd[i][j], xx[i][j]), G[i][j], c2[i][j]);
 
-            if (umax_w > 0x3F000000u /* 0.5f */) {
+#ifndef JSD_NO_PHASE2  /* timing experiments only: results are wrong where u > 1/2 */
+            if (umax_w > JSD_P2_BITS) {
                 // phase 2, packed: for the term pairs in which some lane met u > 1/2, form the log-based
                 // value s * fB(min(a,b)/s) and add (that - series value) where u > 1/2, 0 elsewhere.
                 // Typically a few of the 8 pairs are concerned (one outlier profile of the tile); sparse
@@ -326,6 +330,7 @@ __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdP
                         c2[i][j] = add2(c2[i][j], pk2(u0 > 0.5f ? d0 : 0.f, u1 > 0.5f ? d1 : 0.f));
                     }
             }
+#endif
         }
         // fold the chunk's float32 partial sums (32 non-negative terms each) into float64
 #pragma unroll
