@@ -169,13 +169,16 @@ def cpu_c_port_rates(seqs_sample, n_profile, n_dist, threads):
 
 
 def ncu_traffic(n_contigs):
-    """DRAM bytes per launch of the JSD tile kernel from the committed ncu --set full capture
-    (profiles/r01_traffic.json), when it was taken at this problem size; else None."""
+    """DRAM bytes per launch of the JSD tile kernel from the committed ncu --set full captures
+    (profiles/r01_traffic.json), when one was taken at this problem size; else None."""
     try:
-        rec = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["jsd_tile_kernel"]
-        return rec["dram_bytes_per_launch"] if rec["n_contigs"] == n_contigs else None
+        recs = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["jsd_tile_kernel"]
+        for rec in recs if isinstance(recs, list) else [recs]:
+            if rec["n_contigs"] == n_contigs:
+                return rec["dram_bytes_per_launch"]
     except Exception:
-        return None
+        pass
+    return None
 
 
 def whole_job_pairs_per_s(n_contigs, total_bases, s_per_base, s_per_pair):
@@ -256,6 +259,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=device)
+        engine.bind_host_to_gpu_node(local_rank)  # pinned buffers in the memory next to this GPU (no-op on one node)
     _lib.load()
 
     n_contigs = max(64, int(round(100_000 * args.scale)))
@@ -498,7 +502,7 @@ def run_ours(args):
                 "mufu_lg2_peak_Tops": mufu_peak,
                 "recipe_note": "the kernel spends 12 FP32-pipe operations + 1 MUFU per (pair, dimension) on a "
                                "cancellation-free series; at 100 % FP32-pipe utilisation that is 10/24 = 0.42 of "
-                               "the 10-flop convention (ncu: sm__pipe_fma_cycles_active 75.6 %, profiles/r01_jsd_tile_ncu_summary.txt)",
+                               "the 10-flop convention (ncu: sm__pipe_fma_cycles_active 79.0 %, profiles/r01b_jsd_tile_ncu_summary.txt)",
             },
             "stages": {
                 "profiling_ms_per_launch": prof_ms / max(1, prof_n),

@@ -352,3 +352,36 @@ class PanelStreamer:
             done_events[s].synchronize()
             sink(p0, p1, self.pinned[s][: p1 - p0].numpy())
         return self.pairs_computed
+
+
+# ----------------------------------------------------------------------------
+# Host placement
+# ----------------------------------------------------------------------------
+def bind_host_to_gpu_node(device_index=None):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned buffers it
+    allocates afterwards (first touch) sit in the memory the GPU's PCIe root complex writes to.  One
+    process per GPU under torchrun otherwise floats over both sockets and half of the device-to-host
+    traffic crosses the socket interconnect.  Returns the node number, or None when the topology is
+    not visible (no sysfs entry, single node): then nothing is changed."""
+    import os
+    try:
+        if device_index is None:
+            device_index = torch.cuda.current_device()
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):
+        return None

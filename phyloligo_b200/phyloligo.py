@@ -56,6 +56,7 @@ def ranks():
         torch.cuda.set_device(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        engine.bind_host_to_gpu_node(local)  # pinned panels in the memory next to this GPU
     return dist.get_rank(), dist.get_world_size()
 
 

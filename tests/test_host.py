@@ -142,3 +142,10 @@ def test_savetxt_writes_the_bytes_numpy_writes(tmp_path, dtype):
         io_formats.savetxt(ours, arr)
         np.savetxt(ref, arr, delimiter="\t")
         assert open(ours, "rb").read() == open(ref, "rb").read()
+
+
+def test_host_binding_is_a_no_op_without_topology():
+    before = os.sched_getaffinity(0)
+    assert engine.bind_host_to_gpu_node(0) is None or isinstance(engine.bind_host_to_gpu_node(0), int)
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
