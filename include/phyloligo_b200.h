@@ -207,6 +207,17 @@ int po_ipc_open(const void* h_handle64, void** d_base);
 int po_ipc_close(void* d_base);
 
 /*
+ * Strided block copy between any two of device / pinned host memory (one DMA, no staging):
+ * `rows` rows of `width` bytes, row pitches in bytes.  This is how finished parts of the matrix
+ * leave the device -- the row slices output[s] = ... of the reference's block-row workers
+ * (bin/phyloligo.py:202, 207, 212, 217, 222) -- without waiting for whole rows: a row panel's
+ * part right of the diagonal and the mirrored column block below it are both final as soon as
+ * the panel's tiles are done.  Asynchronous on `stream` when the host side is pinned.
+ */
+int po_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width,
+                    int64_t rows, po_stream_t stream);
+
+/*
  * Text matrix writer on the host -- replaces np.savetxt(path, M, delimiter="\t") at
  * bin/phyloligo.py:1059-1066 (the -o distance matrix and the -q frequency file): "%.18e"
  * fields of the float64 value of every entry, tab separated, '\n' rows, no header; nan / inf /

@@ -313,6 +313,23 @@ int po_ipc_close(void* d_base) {
     return PO_OK;
 }
 
+int po_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width, int64_t rows,
+                    po_stream_t stream) {
+    if (width < 0 || rows < 0 || dst_pitch < width || src_pitch < width) {
+        set_error("po_copy2d_async: bad geometry (width %lld, rows %lld, pitches %lld / %lld)", (long long)width,
+                  (long long)rows, (long long)dst_pitch, (long long)src_pitch);
+        return PO_ERR_ARG;
+    }
+    if (width == 0 || rows == 0) return PO_OK;
+    if (!dst || !src) {
+        set_error("po_copy2d_async: NULL pointer");
+        return PO_ERR_ARG;
+    }
+    PO_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width, (size_t)rows,
+                                    cudaMemcpyDefault, (cudaStream_t)stream));
+    return PO_OK;
+}
+
 int64_t po_launch_count(void) { return g_launches.load(); }
 
 int po_timing_enable(int on) {

@@ -354,6 +354,60 @@ class PanelStreamer:
         return self.pairs_computed
 
 
+def copy2d(dst, src, stream=None):
+    """dst[...] = src for two 2-D views of equal shape and dtype whose rows are contiguous
+    (stride(1) == 1): one strided DMA (po_copy2d_async), no temporaries.  Either side may be a
+    device tensor or a pinned host tensor."""
+    lib = _lib.load()
+    if dst.shape != src.shape or dst.dtype != src.dtype or dst.dim() != 2:
+        raise PhyloligoError("copy2d: views must be 2-D with equal shape and dtype")
+    rows, cols = int(dst.shape[0]), int(dst.shape[1])
+    if rows == 0 or cols == 0:
+        return
+    if (cols > 1 and (dst.stride(1) != 1 or src.stride(1) != 1)):
+        raise PhyloligoError("copy2d: rows must be contiguous")
+    es = dst.element_size()
+    st = C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+    rc = lib.po_copy2d_async(_ptr(dst), int(dst.stride(0)) * es, _ptr(src), int(src.stride(0)) * es, cols * es, rows, st)
+    _lib.check(rc, "po_copy2d_async")
+
+
+def matrix_to_host(X, metric, host, out_dtype=torch.float32, panel_rows=4096, prepared=None, device_matrix=None):
+    """The whole symmetric n x n matrix of profiles X into the host tensor `host` (n x n, pinned).
+
+    The device keeps the matrix resident (4 n^2 bytes); row panels are computed top to bottom, upper
+    triangle + mirror.  As soon as panel p = rows [r0, r1) is done, two blocks are final and leave
+    on the copy stream while panel p+1 computes: the panel's rows from column r0 on, and the
+    mirrored column block [r1, n) x [r0, r1) below it.  What has become final is always
+    proportional to what has been computed, so the PCIe link never waits for the expensive
+    top panels (copying whole rows only, the first third of the matrix runs at kernel speed
+    and the link idles).  Returns the number of bytes copied to the host."""
+    device = require_cuda()
+    P, aux, dim = prepared if prepared is not None else prepare(X, metric)
+    n = int(P.shape[0])
+    if tuple(host.shape) != (n, n) or host.dtype != out_dtype or not host.is_pinned():
+        raise PhyloligoError("matrix_to_host: host must be a pinned (n, n) tensor of the output dtype")
+    full = device_matrix if device_matrix is not None else torch.empty((n, n), dtype=out_dtype, device=device)
+    if tuple(full.shape) != (n, n) or full.dtype != out_dtype:
+        raise PhyloligoError("matrix_to_host: device_matrix must be (n, n) of the output dtype")
+    step = max(TILE, (int(panel_rows) // TILE) * TILE)
+    compute = torch.cuda.current_stream()
+    copy_stream = torch.cuda.Stream()
+    copied = 0
+    for r0 in range(0, n, step):
+        r1 = min(n, r0 + step)
+        distance_block(metric, P, aux, dim, r0, r1, 0, n, full, 0, 0, FLAG_SKIP_LOWER | FLAG_MIRROR)
+        ready = torch.cuda.Event()
+        ready.record(compute)
+        copy_stream.wait_event(ready)
+        copy2d(host[r0:r1, r0:], full[r0:r1, r0:], copy_stream)
+        copy2d(host[r1:, r0:r1], full[r1:, r0:r1], copy_stream)
+        copied += ((r1 - r0) * (n - r0) + (n - r1) * (r1 - r0)) * full.element_size()
+    compute.wait_stream(copy_stream)
+    full.record_stream(copy_stream)
+    return copied
+
+
 # ----------------------------------------------------------------------------
 # Host placement
 # ----------------------------------------------------------------------------

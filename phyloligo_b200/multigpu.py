@@ -62,6 +62,7 @@ class BlockRows:
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.peers = None
         self.staging = None
+        self._copy_stream = None
         if world > 1 and self.exchange == "peer":
             self.peers = engine.PeerRows(self.matrix, rank, world)
         elif world > 1:
@@ -88,14 +89,28 @@ class BlockRows:
     def upper_area(self):
         return sharding.upper_area(self.ranges, self.rank, self.world, self.n)
 
-    def compute(self, metric, P, aux, dim):
-        """Launch this rank's tiles; on return (in stream order) `matrix` holds its complete rows."""
+    def compute(self, metric, P, aux, dim, host_rows=None):
+        """Launch this rank's tiles; on return (in stream order) `matrix` holds its complete rows.
+
+        With `host_rows` (a pinned [rows_owned x n] tensor) the rows also go to the host: the part of
+        a block row from its diagonal block rightwards is written by this rank only, so it leaves on
+        the copy stream as soon as that block row's launches are done, overlapping the next block
+        row's tiles; the part left of the diagonal block is written by the other ranks and leaves
+        after the closing barrier.  Returns `matrix`."""
         n = self.n
+        compute_stream = torch.cuda.current_stream()
+        if host_rows is not None:
+            if tuple(host_rows.shape) != tuple(self.matrix.shape) or not host_rows.is_pinned():
+                raise RuntimeError("host_rows must be a pinned tensor of the shape of BlockRows.matrix")
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream()
         if self.peers is not None:
             self._device_barrier()  # the consumers of the previous result are done with the rows
-        for i in self.my_ranges:
+        for k, i in enumerate(self.my_ranges):
             a, b = self.ranges[i]
             rows = self.out_rows[i]
+            if host_rows is not None and k > 0:
+                self._ship(host_rows, self.my_ranges[k - 1], compute_stream, right=True)
             engine.distance_block(metric, P, aux, dim, a, b, a, b, rows, a, 0, FLAG_SKIP_LOWER | FLAG_MIRROR)
             if b >= n:
                 continue
@@ -114,8 +129,27 @@ class BlockRows:
                 addr = base + self.offsets[q] * n * self.esize
                 engine.distance_block(metric, P, aux, dim, a, b, aq, bq, rows, a, 0, FLAG_MIRROR,
                                       mirror=addr, mirror_row0=aq, mirror_col0=0, mirror_ld=n)
+        if host_rows is not None and self.my_ranges:
+            self._ship(host_rows, self.my_ranges[-1], compute_stream, right=True)
         if self.peers is not None:
             self._device_barrier()
         elif self.world > 1:
             sharding.exchange_transposed(self.staging, self.ranges, self.rank, self.world, self.out_rows)
+        if host_rows is not None:
+            for i in self.my_ranges:
+                self._ship(host_rows, i, compute_stream, right=False)
+            compute_stream.wait_stream(self._copy_stream)
         return self.matrix
+
+    def _ship(self, host_rows, i, compute_stream, right):
+        """Copy block row i to the host on the copy stream: its columns from the diagonal block on
+        (`right`) or the ones left of it, once everything launched so far on the compute stream is done."""
+        a, b = self.ranges[i]
+        off = self.offsets[i]
+        ready = torch.cuda.Event()
+        ready.record(compute_stream)
+        self._copy_stream.wait_event(ready)
+        if right:
+            engine.copy2d(host_rows[off:off + (b - a), a:], self.matrix[off:off + (b - a), a:], self._copy_stream)
+        else:
+            engine.copy2d(host_rows[off:off + (b - a), :a], self.matrix[off:off + (b - a), :a], self._copy_stream)

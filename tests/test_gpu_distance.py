@@ -232,3 +232,30 @@ def test_tensor_core_spearman_is_exact(n, dim, monkeypatch):
     m = ~np.isnan(want)
     assert np.abs(sub[m] - want[m]).max() < 1e-12
     assert sub[5, 6] == 2.0 and sub[5, 5] == 0.0
+
+
+@pytest.mark.parametrize("metric,n", [("JSD", 700), ("EuclGram", 520), ("SC", 300)])
+def test_matrix_to_host_ships_finished_blocks(metric, n):
+    """engine.matrix_to_host: panels' right parts + mirrored column blocks by strided DMA
+    (po_copy2d_async) give exactly the resident matrix in pinned host memory."""
+    rng = np.random.default_rng(n)
+    X = torch.from_numpy(rng.dirichlet(np.ones(256), size=n).astype(np.float32)).cuda()
+    want = engine.distance_matrix_device(X, metric, torch.float32, symmetric=True).cpu()
+    host = torch.full((n, n), -1.0, dtype=torch.float32).pin_memory()
+    copied = engine.matrix_to_host(X, metric, host, torch.float32, panel_rows=128)
+    torch.cuda.synchronize()
+    assert copied == n * n * 4
+    assert torch.equal(host, want)
+    with pytest.raises(Exception):
+        engine.matrix_to_host(X, metric, torch.empty((n, n), dtype=torch.float32), torch.float32)  # not pinned
+
+
+def test_copy2d_strided_views():
+    a = torch.arange(40 * 50, dtype=torch.float32, device="cuda").reshape(40, 50)
+    h = torch.zeros((40, 50), dtype=torch.float32).pin_memory()
+    engine.copy2d(h[5:30, 7:41], a[5:30, 7:41])
+    torch.cuda.synchronize()
+    want = torch.zeros((40, 50))
+    want[5:30, 7:41] = a[5:30, 7:41].cpu()
+    assert torch.equal(h, want)
+    engine.copy2d(h[0:0, :], a[0:0, :])  # empty block: nothing to do

@@ -22,10 +22,12 @@ for exchange in ("peer", "nccl"):
         job.matrix.fill_(float("nan"))
         torch.cuda.synchronize()
         dist.barrier()
-        for _ in range(2):  # twice: the second pass overwrites live rows while peers may still read them
-            job.compute(metric, P, aux, d)
+        host = torch.full(tuple(job.matrix.shape), -1.0, dtype=torch.float32).pin_memory()
+        for it in range(2):  # twice: the second pass overwrites live rows while peers may still read them
+            job.compute(metric, P, aux, d, host_rows=host if it else None)  # second pass also ships the rows to the host
         torch.cuda.synchronize()
         ok = all(torch.equal(job.out_rows[i], full[job.ranges[i][0]:job.ranges[i][1]]) for i in job.out_rows)
+        ok = ok and (job.rows_owned == 0 or torch.equal(host[:job.rows_owned], job.matrix[:job.rows_owned].cpu()))
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
