@@ -311,6 +311,8 @@ __device__ __forceinline__ void g_tmem_ld16(unsigned taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void g_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+enum GramMode { GM_EUCL = 0, GM_SC = 1 };
+
 struct GramParams {
     const unsigned char* P;  // operand blocks [n/128 groups][nkb][hi | lo][16 KB]
     const float* X32;        // float32 copy of the profiles, row pitch nkb * 64
@@ -327,7 +329,118 @@ struct GramParams {
     unsigned flags;
 };
 
-enum GramMode { GM_EUCL = 0, GM_SC = 1 };
+
+// Epilogue of one tile.  Warp w owns TMEM lanes 32 (w & 3) .. +31 (the rows a warp may read) and the
+// 32 columns 32 (w >> 2) .. +31, in two chunks of 16.  Mirrored entries are stored straight from the
+// registers (lanes = consecutive rows = consecutive addresses of the mirrored row); the direct
+// entries go through a 32 x 33 shared-memory transpose so that a warp stores 128 contiguous bytes of
+// one output row per instruction.  The operand ring is free by now.  Addresses are one 64-bit base
+// per thread plus small offsets; INTERIOR tiles carry no per-entry bounds tests.
+template <typename OUT_T, int MODE, bool INTERIOR>
+__device__ __forceinline__ void gram_epilogue(const GramParams& p, unsigned tmem, int64_t row_base, int64_t col_base,
+                                              const double* s_nb, unsigned char* gsmem) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int lq = warp & 3, cq = warp >> 2;
+    const int r = lq * 32 + lane;  // tile row == TMEM lane
+    const int64_t grow = row_base + r;
+    const bool row_ok = INTERIOR || (grow >= p.row0 && grow < p.row1);
+    const double na = (INTERIOR || grow < p.n) ? p.aux[grow] : 0.0;
+    const bool do_mirror = (p.flags & PO_FLAG_MIRROR) && row_base + GT <= col_base;
+    const bool diag_tile = row_base == col_base;
+    const int64_t ldx32 = (int64_t)p.nkb * GK;
+    OUT_T* tbuf = reinterpret_cast<OUT_T*>(gsmem) + (size_t)warp * (32 * 33);
+    // mirrored entry (c, r) of this thread's row r and tile column 0
+    OUT_T* mir_col0 = reinterpret_cast<OUT_T*>(p.mir) + (col_base - p.mir_row0) * p.ld_mir + (grow - p.mir_col0);
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        const int c0 = cq * 32 + half * 16;
+        uint32_t vh[16], vx[16], vy[16];
+        const unsigned ta = tmem + ((unsigned)(lq * 32) << 16) + (unsigned)c0;
+        g_tmem_ld16(ta, vh);
+        g_tmem_ld16(ta + GT, vx);
+        g_tmem_ld16(ta + 2 * GT, vy);
+        g_tmem_wait_ld();
+        OUT_T val[16];
+        unsigned cancel = 0u;  // columns of this chunk whose Gram form cancelled too much
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const double nb = s_nb[c0 + j];
+            if (MODE == GM_SC) {
+                // exact integer dot product of the centred doubled ranks, then 1 - rho as K_SC does
+                const long long t = 4096ll * (long long)__uint_as_float(vh[j]) + 64ll * (long long)__uint_as_float(vx[j]) +
+                                    (long long)__uint_as_float(vy[j]);
+                const double den = sqrt(na * nb);
+                const double v = (den == 0.0) ? __longlong_as_double(0x7FF8000000000000ll)  // scipy: NaN for a constant row
+                                              : 1.0 - (double)t / den;
+                val[j] = (OUT_T)v;
+                continue;
+            }
+            const float dot = __uint_as_float(vh[j]) + (__uint_as_float(vx[j]) + __uint_as_float(vy[j]));
+            const double nsum = na + nb;
+            double d2 = nsum - 2.0 * (double)dot;
+            const bool on_diag = diag_tile && r == c0 + j;
+            const bool inside = INTERIOR || (row_ok && col_base + c0 + j >= p.col0 && col_base + c0 + j < p.col1);
+            if (inside && !on_diag && d2 * 256.0 < nsum) cancel |= 1u << j;
+            d2 = (d2 > 0.0 ? d2 : 0.0) * GUNSCALE;
+            if (sizeof(OUT_T) == 8) val[j] = (OUT_T)sqrt(d2);
+            else val[j] = (OUT_T)sqrtf((float)d2);
+            if (on_diag) val[j] = (OUT_T)0;  // sklearn forces an exact zero diagonal
+        }
+        // exact recomputation, one entry at a time, by the whole warp
+        unsigned lanes = (MODE == GM_EUCL) ? __ballot_sync(0xFFFFFFFFu, cancel != 0u) : 0u;
+        while (lanes) {
+            const int l = __ffs(lanes) - 1;
+            lanes &= lanes - 1;
+            unsigned m = __shfl_sync(0xFFFFFFFFu, cancel, l);
+            const int64_t er = row_base + lq * 32 + l;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const float* xa = p.X32 + er * ldx32;
+                const float* xb = p.X32 + (col_base + c0 + j) * ldx32;
+                double acc = 0.0;
+                for (int64_t k0 = 0; k0 < ldx32; k0 += 1024) {  // float32 partial sums of <= 32 terms per lane
+                    float part = 0.f;
+                    const int64_t k1 = min(ldx32, k0 + 1024);
+                    for (int64_t k = k0 + lane; k < k1; k += 32) {
+                        const float d = xa[k] - xb[k];
+                        part = fmaf(d, d, part);
+                    }
+                    acc += (double)part;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+                if (lane == l) {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj)
+                        if (jj == j) val[jj] = (sizeof(OUT_T) == 8) ? (OUT_T)sqrt(acc) : (OUT_T)sqrtf((float)acc);
+                }
+            }
+        }
+        if (do_mirror) {
+            OUT_T* mp = mir_col0 + (int64_t)c0 * p.ld_mir;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (INTERIOR || (row_ok && col_base + c0 + j >= p.col0 && col_base + c0 + j < p.col1)) *mp = val[j];
+                mp += p.ld_mir;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) tbuf[lane * 33 + half * 16 + j] = val[j];
+    }
+    __syncwarp();
+    {
+        const int64_t gcol = col_base + cq * 32 + lane;
+        const bool col_ok = INTERIOR || (gcol >= p.col0 && gcol < p.col1);
+        const int64_t gr0 = row_base + lq * 32;
+        OUT_T* op = reinterpret_cast<OUT_T*>(p.out) + (gr0 - p.out_row0) * p.ld_out + (gcol - p.out_col0);
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+            if (INTERIOR || (col_ok && gr0 + rr >= p.row0 && gr0 + rr < p.row1)) *op = tbuf[rr * 33 + lane];
+            op += p.ld_out;
+        }
+    }
+}
 
 template <typename OUT_T, int MODE>
 __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams p) {
@@ -413,12 +526,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
     }
     __syncwarp();
 
-    // ===== epilogue: warp w owns TMEM lanes 32 (w & 3) .. +31 (the rows a warp may read) and the
-    // 32 columns 32 (w >> 2) .. +31, in two chunks of 16.  Mirrored entries are stored straight from
-    // the registers (lanes = consecutive rows = consecutive addresses of the mirrored row); the
-    // direct entries go through a 32 x 33 shared-memory transpose so that a warp stores 128
-    // contiguous bytes of one output row per instruction.  The operand ring is free by now.
-    const int lq = warp & 3, cq = warp >> 2;
+    // ===== epilogue (gram_epilogue): all 16 warps =====
     if (tid < GT) {
         const int64_t gc = col_base + tid;
         s_nb[tid] = (gc < p.n) ? p.aux[gc] : 0.0;
@@ -426,99 +534,12 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
     __syncthreads();
     g_mbar_wait(accum, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int r = lq * 32 + lane;  // tile row == TMEM lane
-    const int64_t grow = row_base + r;
-    const bool row_ok = grow >= p.row0 && grow < p.row1;
-    const double na = (grow < p.n) ? p.aux[grow] : 0.0;
-    OUT_T* out = reinterpret_cast<OUT_T*>(p.out);
-    OUT_T* mir = reinterpret_cast<OUT_T*>(p.mir);
-    const bool do_mirror = (p.flags & PO_FLAG_MIRROR) && row_base + GT <= col_base;
-    const int64_t ldx32 = (int64_t)nkb * GK;
-    OUT_T* tbuf = reinterpret_cast<OUT_T*>(gsmem) + (size_t)warp * (32 * 33);
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        const int c0 = cq * 32 + half * 16;
-        uint32_t vh[16], vx[16], vy[16];
-        const unsigned ta = tmem + ((unsigned)(lq * 32) << 16) + (unsigned)c0;
-        g_tmem_ld16(ta, vh);
-        g_tmem_ld16(ta + GT, vx);
-        g_tmem_ld16(ta + 2 * GT, vy);
-        g_tmem_wait_ld();
-        OUT_T val[16];
-        unsigned cancel = 0u;  // columns of this chunk whose Gram form cancelled too much
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int64_t gcol = col_base + c0 + j;
-            const double nb = s_nb[c0 + j];
-            if (MODE == GM_SC) {
-                // exact integer dot product of the centred doubled ranks, then 1 - rho as K_SC does
-                const long long t = 4096ll * (long long)__uint_as_float(vh[j]) + 64ll * (long long)__uint_as_float(vx[j]) +
-                                    (long long)__uint_as_float(vy[j]);
-                const double den = sqrt(na * nb);
-                const double v = (den == 0.0) ? __longlong_as_double(0x7FF8000000000000ll)  // scipy: NaN for a constant row
-                                              : 1.0 - (double)t / den;
-                val[j] = (OUT_T)v;
-                continue;
-            }
-            const float dot = __uint_as_float(vh[j]) + (__uint_as_float(vx[j]) + __uint_as_float(vy[j]));
-            double d2 = na + nb - 2.0 * (double)dot;
-            const bool inside = row_ok && gcol >= p.col0 && gcol < p.col1;
-            if (inside && grow != gcol && d2 * 256.0 < na + nb) cancel |= 1u << j;
-            d2 = (d2 > 0.0 ? d2 : 0.0) * GUNSCALE;
-            if (sizeof(OUT_T) == 8) val[j] = (OUT_T)sqrt(d2);
-            else val[j] = (OUT_T)sqrtf((float)d2);
-            if (grow == gcol) val[j] = (OUT_T)0;  // sklearn forces an exact zero diagonal
-        }
-        // exact recomputation, one entry at a time, by the whole warp
-        unsigned lanes = (MODE == GM_EUCL) ? __ballot_sync(0xFFFFFFFFu, cancel != 0u) : 0u;
-        while (lanes) {
-            const int l = __ffs(lanes) - 1;
-            lanes &= lanes - 1;
-            unsigned m = __shfl_sync(0xFFFFFFFFu, cancel, l);
-            const int64_t er = row_base + lq * 32 + l;
-            while (m) {
-                const int j = __ffs(m) - 1;
-                m &= m - 1;
-                const float* xa = p.X32 + er * ldx32;
-                const float* xb = p.X32 + (col_base + c0 + j) * ldx32;
-                double acc = 0.0;
-                for (int64_t k0 = 0; k0 < ldx32; k0 += 1024) {  // float32 partial sums of <= 32 terms per lane
-                    float part = 0.f;
-                    const int64_t k1 = min(ldx32, k0 + 1024);
-                    for (int64_t k = k0 + lane; k < k1; k += 32) {
-                        const float d = xa[k] - xb[k];
-                        part = fmaf(d, d, part);
-                    }
-                    acc += (double)part;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-                if (lane == l) {
-#pragma unroll
-                    for (int jj = 0; jj < 16; ++jj)
-                        if (jj == j) val[jj] = (sizeof(OUT_T) == 8) ? (OUT_T)sqrt(acc) : (OUT_T)sqrtf((float)acc);
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int64_t gcol = col_base + c0 + j;
-            if (do_mirror && row_ok && gcol >= p.col0 && gcol < p.col1)
-                mir[(gcol - p.mir_row0) * p.ld_mir + (grow - p.mir_col0)] = val[j];
-            tbuf[lane * 33 + half * 16 + j] = val[j];
-        }
-    }
-    __syncwarp();
-    {
-        const int64_t gcol = col_base + cq * 32 + lane;
-        const bool col_ok = gcol >= p.col0 && gcol < p.col1;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-            const int64_t gr = row_base + lq * 32 + rr;
-            if (col_ok && gr >= p.row0 && gr < p.row1)
-                out[(gr - p.out_row0) * p.ld_out + (gcol - p.out_col0)] = tbuf[rr * 33 + lane];
-        }
-    }
+    // tiles wholly inside the requested block (all but the ragged edges) skip the per-entry bounds tests
+    const bool interior = row_base >= p.row0 && row_base + GT <= p.row1 && col_base >= p.col0 && col_base + GT <= p.col1;
+    if (interior)
+        gram_epilogue<OUT_T, MODE, true>(p, tmem, row_base, col_base, s_nb, gsmem);
+    else
+        gram_epilogue<OUT_T, MODE, false>(p, tmem, row_base, col_base, s_nb, gsmem);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
