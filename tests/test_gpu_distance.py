@@ -259,3 +259,64 @@ def test_copy2d_strided_views():
     want[5:30, 7:41] = a[5:30, 7:41].cpu()
     assert torch.equal(h, want)
     engine.copy2d(h[0:0, :], a[0:0, :])  # empty block: nothing to do
+
+
+@pytest.mark.parametrize("metric,n,dim", [("JSD", 100_000, 256), ("EuclGram", 50_000, 4096), ("SC", 20_000, 256)])
+def test_full_size_matrix_properties(metric, n, dim):
+    """BASELINE.json sizes (C2 JSD 100k x 256, C3 Eucl 50k x 4096, C4 SC 20k x 256) through
+    size-independent properties: exact diagonal, bitwise symmetry, value range, sampled entries against
+    the float64 oracle, and sampled row panels recomputed without the symmetry shortcut."""
+    need = n * n * 4 + 6 * n * dim * 4 + (2 << 30)
+    free, _ = torch.cuda.mem_get_info()
+    if free < need:
+        pytest.skip("needs %.0f GB of free HBM" % (need / 1e9))
+    g = torch.Generator(device="cuda").manual_seed(n + dim)
+    X = torch.rand((n, dim), device="cuda", generator=g) ** 3
+    X[::97, ::5] = 0.0                      # exact zeros, as sparse profiles have
+    if metric == "SC":
+        X = torch.round(X * 40) / 40        # tie-heavy
+    X /= X.sum(dim=1, keepdim=True)
+    X[12345 % n] = 0.0                      # an empty record's all-zero row
+    M = engine.distance_matrix_device(X, metric, torch.float32, symmetric=True)
+    diag = torch.diagonal(M)
+    zero_row = 12345 % n
+    if metric == "SC":
+        assert torch.isnan(M[zero_row]).all() and torch.isnan(M[:, zero_row]).all()
+        keep = torch.ones(n, dtype=torch.bool, device="cuda")
+        keep[zero_row] = False
+        assert (diag[keep] == 0).all()
+    else:
+        assert (diag == 0).all()
+    for r0 in range(0, n, 8192):            # bitwise symmetry, panel by panel
+        r1 = min(n, r0 + 8192)
+        a, b = M[r0:r1], M[:, r0:r1].T
+        assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+    finite = M[~torch.isnan(M)] if metric == "SC" else M
+    lo, hi = float(finite.min()), float(finite.max())
+    if metric == "JSD":
+        assert lo == 0.0 and hi <= np.log(2) * (1 + 1e-6)
+        others = torch.ones(n, dtype=torch.bool, device="cuda")
+        others[zero_row] = False
+        assert torch.allclose(M[zero_row][others], torch.full((n - 1,), np.log(2) / 2, device="cuda"), rtol=2e-6)
+    elif metric == "SC":
+        assert lo > -1e-6 and hi < 2.0 + 1e-6
+    else:
+        assert lo == 0.0
+    # sampled entries against the oracle in float64
+    rng = np.random.default_rng(5)
+    ii, jj = rng.integers(0, n, 600), rng.integers(0, n, 600)
+    Xh = X[np.unique(np.concatenate([ii, jj]))].double().cpu().numpy()
+    index = {v: k for k, v in enumerate(np.unique(np.concatenate([ii, jj])))}
+    got = M[torch.from_numpy(ii).cuda(), torch.from_numpy(jj).cuda()].cpu().numpy().astype(np.float64)
+    fn = {"JSD": po.JSD, "EuclGram": po.Eucl, "SC": po.SC}[metric]
+    want = np.array([fn(Xh[index[i]], Xh[index[j]]) for i, j in zip(ii, jj)])
+    ok = ~np.isnan(want)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    tol = {"JSD": 2e-6, "EuclGram": RTOL_TC, "SC": 2e-6}[metric]  # float32 output
+    assert np.allclose(got[ok], want[ok], rtol=tol, atol=1e-7), np.abs(got[ok] - want[ok]).max()
+    # row panels recomputed as plain block rows (every entry computed, no mirror)
+    P, aux, d = engine.prepare(X, metric)
+    for r0 in (0, (n // 2) // 128 * 128, n - 300):
+        blk = torch.empty((300, n), dtype=torch.float32, device="cuda")
+        engine.distance_block(metric, P, aux, d, r0, r0 + 300, 0, n, blk, r0, 0)
+        assert torch.equal(torch.nan_to_num(blk, nan=-7.0), torch.nan_to_num(M[r0:r0 + 300], nan=-7.0))
