@@ -207,6 +207,24 @@ int po_ipc_open(const void* h_handle64, void** d_base);
 int po_ipc_close(void* d_base);
 
 /*
+ * Kount.py's sliding-window stage (bin/Kount.py:274-453).  Every window of every contig is a
+ * virtual record of po_profile_batch (d_begin / d_end = the window's byte range in a text whose
+ * sequences carry no line breaks).  Two small per-window kernels complete it:
+ *   po_window_count_byte  occurrences of one byte value in every window -- the
+ *                         seq.count('N') / len(seq) <= n_max_freq_in_windows filter (:294)
+ *   po_window_distances   distance of every window profile (float64 [n x dim], row pitch ld) to ONE
+ *                         reference profile d_ref[dim], float64 out[n]: the 1-D forms dispatched by
+ *                         compute_distance_joblib (:317-324).  metric 0 = JSD (:94-123, x1000),
+ *                         1 = KL (:71-86), 2 = Eucl (:88-92, x1000); NaN / Inf terms are zeroed
+ *                         term by term (posdef_check_value, :67-69).
+ */
+enum po_window_metric { PO_W_JSD = 0, PO_W_KL = 1, PO_W_EUCL = 2 };
+int po_window_count_byte(const uint8_t* d_text, const int64_t* d_begin, const int64_t* d_end, int64_t n,
+                         int value, int64_t* d_counts, po_stream_t stream);
+int po_window_distances(int metric, const double* d_freq, int64_t n, int64_t dim, int64_t ld,
+                        const double* d_ref, double* d_out, po_stream_t stream);
+
+/*
  * Strided block copy between any two of device / pinned host memory (one DMA, no staging):
  * `rows` rows of `width` bytes, row pitches in bytes.  This is how finished parts of the matrix
  * leave the device -- the row slices output[s] = ... of the reference's block-row workers

@@ -26,7 +26,7 @@ TILE = 128  # largest kernel tile edge: row panels and rank boundaries are multi
 EXPORTED = [
     "po_version", "po_last_error", "po_device_info", "po_pattern_info", "po_fasta_index_host",
     "po_profile_batch", "po_prepared_row_bytes", "po_prepared_bytes", "po_prepare_profiles", "po_distance_block", "po_distance_block_ex",
-    "po_ipc_export", "po_ipc_open", "po_ipc_close", "po_savetxt_host", "po_copy2d_async", "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read", "po_microbench",
+    "po_ipc_export", "po_ipc_open", "po_ipc_close", "po_savetxt_host", "po_copy2d_async", "po_window_count_byte", "po_window_distances", "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read", "po_microbench",
 ]
 
 
@@ -78,6 +78,10 @@ def load():
     lib.po_ipc_open.restype = i32
     lib.po_ipc_close.argtypes = [vp]
     lib.po_ipc_close.restype = i32
+    lib.po_window_count_byte.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    lib.po_window_count_byte.restype = i32
+    lib.po_window_distances.argtypes = [i32, vp, i64, i64, i64, vp, vp, vp]
+    lib.po_window_distances.restype = i32
     lib.po_copy2d_async.argtypes = [vp, i64, vp, i64, i64, i64, vp]
     lib.po_copy2d_async.restype = i32
     lib.po_savetxt_host.argtypes = [C.c_char_p, vp, i64, i64, i64, i32, i32]

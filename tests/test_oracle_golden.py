@@ -142,3 +142,30 @@ def test_profile_properties():
             assert tp == tm == sum(r - P + 1 for r in runs)
             junction = cb - cp - cm
             assert (junction >= 0).all() and junction.sum() <= P - 1
+
+
+def test_kount_oracle_replays_the_reference_goldens(tmp_path):
+    """oracle/kount_oracle.py against outputs of the reference's own Kount.py function bodies
+    (tests/golden/make_kount_golden.py): window coordinates exact, distances to 1e-12."""
+    import json
+    import os
+
+    from oracle import kount_oracle as ko
+
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kount_golden.json")))
+    assert len(cases) >= 4
+    for ci, case in enumerate(cases):
+        path = os.path.join(tmp_path, "asm%d.fasta" % ci)
+        with open(path, "w") as fh:
+            fh.write(case["fasta"])
+        records = ko.read_records(path)
+        mcp = ko.compute_whole_composition(records, case["pattern"], case["strand"])
+        want_mcp = np.array([float.fromhex(v) for v in case["mcp"]])
+        assert np.array_equal(mcp, want_mcp)
+        for dist, rows in case["rows"].items():
+            got = ko.sliding_windows_distances(records, mcp, dist, case["pattern"], case["window"], case["step"],
+                                               case["strand"], case["n_max"])
+            assert [r[:3] for r in got] == [r[:3] for r in rows]
+            g = np.array([r[3] for r in got])
+            w = np.array([float.fromhex(r[3]) for r in rows])
+            assert np.allclose(g, w, rtol=1e-12, atol=1e-15), (dist, np.abs(g - w).max())
