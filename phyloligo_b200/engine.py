@@ -269,6 +269,13 @@ def pair_distance(a, b, metric):
     return float(out[0, 1].item())
 
 
+def auto_panel_rows(n, element_size=4, target_bytes=256 << 20):
+    """Rows per panel so that one pinned panel buffer is about 256 MB (page-locking host memory costs
+    ~0.5 s per GB; the copies are long enough to run at link speed well below that)."""
+    rows = target_bytes // max(1, int(n) * int(element_size))
+    return int(max(TILE, min(4096, (rows // TILE) * TILE)))
+
+
 class PanelStreamer:
     """Compute the matrix in row panels and stream each finished panel to the host.
 
@@ -279,14 +286,16 @@ class PanelStreamer:
     full rows into one of two panel buffers.
     """
 
-    def __init__(self, X, metric, out_dtype=torch.float32, panel_rows=4096, symmetric=None, rows=None):
+    def __init__(self, X, metric, out_dtype=torch.float32, panel_rows=None, symmetric=None, rows=None):
         self.device = require_cuda()
         self.metric = metric
         self.P, self.aux, self.dim = prepare(X, metric)
         self.n = int(self.P.shape[0])
         self.out_dtype = out_dtype
-        self.panel_rows = max(TILE, (int(panel_rows) // TILE) * TILE)
         esize = 4 if out_dtype == torch.float32 else 8
+        if panel_rows is None:
+            panel_rows = auto_panel_rows(self.n, esize)
+        self.panel_rows = max(TILE, (int(panel_rows) // TILE) * TILE)
         if symmetric is None:
             free, _ = torch.cuda.mem_get_info()
             symmetric = rows is None and self.n * self.n * esize < 0.6 * free

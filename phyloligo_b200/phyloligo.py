@@ -31,7 +31,7 @@ import torch
 from . import engine, io_formats, phylodist
 from ._lib import PhyloligoError, METRICS, TILE
 
-PANEL_ROWS = 4096
+PANEL_ROWS = None  # rows per streamed panel; None = engine.auto_panel_rows (about 256 MB per pinned buffer)
 
 
 def remove_folder(folder):
@@ -380,13 +380,14 @@ def _stream_rows_impl(sink, X, metric, n, rank, world):
         P, aux, dim = engine.prepare(X, metric)
         job = multigpu.BlockRows(n, torch.float32, rank, world)
         job.compute(metric, P, aux, dim)
-        pinned = [torch.empty((PANEL_ROWS, n), dtype=torch.float32).pin_memory() for _ in range(2)]
+        panel = PANEL_ROWS or engine.auto_panel_rows(n, 4)
+        pinned = [torch.empty((panel, n), dtype=torch.float32).pin_memory() for _ in range(2)]
         events, pending = [None, None], []
         k = 0
         for i in job.my_ranges:
             a, b = job.ranges[i]
-            for r0 in range(a, b, PANEL_ROWS):
-                r1 = min(b, r0 + PANEL_ROWS)
+            for r0 in range(a, b, panel):
+                r1 = min(b, r0 + panel)
                 slot = k & 1
                 while pending and pending[0][0] == slot:
                     _, p0, p1 = pending.pop(0)

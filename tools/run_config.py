@@ -70,7 +70,7 @@ for metric in metrics:
             checks["sum"] += float(host[:, ::997].sum())   # touch the data (discard sink)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    st = engine.PanelStreamer(X, dev_metric, torch.float32, panel_rows=4096)
+    st = engine.PanelStreamer(X, dev_metric, torch.float32)
     pairs_computed = st.run(sink)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
