@@ -154,6 +154,16 @@ int po_prepare_profiles(int metric, const void* d_X, int dtype, int64_t n, int64
                         void* d_P, double* d_aux, po_stream_t stream);
 
 /*
+ * Rank transform of every profile: average ranks 1..dim, ties sharing the mean of their positions --
+ * the scipy.stats.spearmanr / rankdata step of phylodist.SC (core/phylodist.py:82-85) as a stand-alone
+ * call.  d_X is [n x dim] float32 / float64 with row pitch ldx, d_ranks [n x dim] float64 with row
+ * pitch ldr.  (po_prepare_profiles(PO_SC) runs the same transform and stores it in the layout the
+ * tile kernels read.)
+ */
+int po_rank_transform(const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx, double* d_ranks,
+                      int64_t ldr, po_stream_t stream);
+
+/*
  * One block of the all-by-all distance matrix -- replaces the slice workers
  * distances_loc / *_loc (bin/phyloligo.py:195-222), distances_h5py / *_h5py
  * (:233-301), compute_unpack (:166-171) and the phylodist pair functions Eucl,

@@ -25,7 +25,7 @@ TILE = 128  # largest kernel tile edge: row panels and rank boundaries are multi
 # every symbol include/phyloligo_b200.h declares (tests check the library exports them all)
 EXPORTED = [
     "po_version", "po_last_error", "po_device_info", "po_pattern_info", "po_fasta_index_host",
-    "po_profile_batch", "po_prepared_row_bytes", "po_prepared_bytes", "po_prepare_profiles", "po_distance_block", "po_distance_block_ex",
+    "po_profile_batch", "po_prepared_row_bytes", "po_prepared_bytes", "po_prepare_profiles", "po_rank_transform", "po_distance_block", "po_distance_block_ex",
     "po_ipc_export", "po_ipc_open", "po_ipc_close", "po_savetxt_host", "po_copy2d_async", "po_window_count_byte", "po_window_distances", "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read", "po_microbench",
 ]
 
@@ -82,6 +82,8 @@ def load():
     lib.po_window_count_byte.restype = i32
     lib.po_window_distances.argtypes = [i32, vp, i64, i64, i64, vp, vp, vp]
     lib.po_window_distances.restype = i32
+    lib.po_rank_transform.argtypes = [vp, i32, i64, i64, i64, vp, i64, vp]
+    lib.po_rank_transform.restype = i32
     lib.po_copy2d_async.argtypes = [vp, i64, vp, i64, i64, i64, vp]
     lib.po_copy2d_async.restype = i32
     lib.po_savetxt_host.argtypes = [C.c_char_p, vp, i64, i64, i64, i32, i32]

@@ -222,6 +222,15 @@ int po_prepare_profiles(int metric, const void* d_X, int dtype, int64_t n, int64
     return launch_prepare(metric, d_X, dtype, n, dim, ldx, d_P, d_aux, (cudaStream_t)stream);
 }
 
+int po_rank_transform(const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx, double* d_ranks, int64_t ldr,
+                      po_stream_t stream) {
+    if (n < 0 || dim < 1 || ldx < dim || ldr < dim || (dtype != PO_F32 && dtype != PO_F64) || (n > 0 && (!d_X || !d_ranks))) {
+        set_error("po_rank_transform: bad arguments");
+        return PO_ERR_ARG;
+    }
+    return launch_rank_transform(d_X, dtype, n, dim, ldx, d_ranks, ldr, (cudaStream_t)stream);
+}
+
 static int distance_block_checked(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim,
                                   int64_t row0, int64_t row1, int64_t col0, int64_t col1, void* d_out,
                                   int64_t ld_out, int64_t out_row0, int64_t out_col0, void* d_mir, int64_t ld_mir,

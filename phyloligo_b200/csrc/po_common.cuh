@@ -63,6 +63,9 @@ int launch_profile(const uint8_t* d_text, const int64_t* d_begin, const int64_t*
 int launch_prepare(int metric, const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx,
                    void* d_P, double* d_aux, cudaStream_t stream);
 
+int launch_rank_transform(const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx, double* d_R, int64_t ldr,
+                          cudaStream_t stream);
+
 int launch_distance(int metric, const void* d_P, const double* d_aux, int64_t n, int64_t dim,
                     int64_t row0, int64_t row1, int64_t col0, int64_t col1,
                     void* d_out, int64_t ld_out, int64_t out_row0, int64_t out_col0,

@@ -138,6 +138,39 @@ __global__ void __launch_bounds__(256) prepare_rank_kernel(const void* __restric
     if (threadIdx.x == 0) aux[row] = (double)s_ss;
 }
 
+// Average ranks 1..dim as float64 (scipy.stats.rankdata(method="average")): the stand-alone form of
+// the SC prologue, po_rank_transform.
+template <typename T>
+__global__ void __launch_bounds__(256) rank_average_kernel(const void* __restrict__ X, int64_t dim, int64_t ldx,
+                                                           double* __restrict__ R, int64_t ldr, int dpad) {
+    extern __shared__ __align__(8) unsigned char rank_smem[];
+    const int64_t row = blockIdx.x;
+    rank_transform_row<T>(reinterpret_cast<const T*>(X) + row * ldx, (int)dim, dpad, rank_smem,
+                          [&](int e, int val) { R[row * ldr + e] = 0.5 * (double)(val + (int)dim + 1); });
+}
+
+int launch_rank_transform(const void* d_X, int dtype, int64_t n, int64_t dim, int64_t ldx, double* d_R, int64_t ldr,
+                          cudaStream_t stream) {
+    if (n == 0) return PO_OK;
+    const size_t sm = rank_smem_bytes(dim);
+    if (sm > 200 * 1024 || n > 0x7FFFFFFFll) {
+        set_error("po_rank_transform: %lld rows of dimension %lld are outside the supported envelope", (long long)n,
+                  (long long)dim);
+        return PO_ERR_UNSUPPORTED;
+    }
+    const int dpad = (int)rank_pad(dim);
+    if (dtype == PO_F32) {
+        PO_CUDA_CHECK(cudaFuncSetAttribute(rank_average_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        rank_average_kernel<float><<<(unsigned)n, 256, sm, stream>>>(d_X, dim, ldx, d_R, ldr, dpad);
+    } else {
+        PO_CUDA_CHECK(cudaFuncSetAttribute(rank_average_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        rank_average_kernel<double><<<(unsigned)n, 256, sm, stream>>>(d_X, dim, ldx, d_R, ldr, dpad);
+    }
+    count_launch(2);
+    PO_LAUNCH_CHECK("rank_average_kernel");
+    return PO_OK;
+}
+
 // KT: packed order-relation masks.
 template <typename T>
 __global__ void __launch_bounds__(256) prepare_kendall_kernel(const void* __restrict__ X, int64_t n, int64_t dim,

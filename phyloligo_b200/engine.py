@@ -88,7 +88,14 @@ def text_to_device(text, device=None, non_blocking=False):
     if isinstance(text, torch.Tensor):
         src = text
     else:
-        src = torch.from_numpy(as_u8(text))
+        arr = as_u8(text)
+        if not arr.flags.writeable:  # read-only views (bytes, read-only mappings) are only read from
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                src = torch.from_numpy(arr)
+        else:
+            src = torch.from_numpy(arr)
     n = src.shape[0]
     dst = torch.empty(n + 64, dtype=torch.uint8, device=device)
     dst[:n].copy_(src, non_blocking=non_blocking)
@@ -174,6 +181,20 @@ def prepare(X, metric):
                                  n, dim, dim, _ptr(P), _ptr(aux), _stream())
     _lib.check(rc, "po_prepare_profiles")
     return P, aux, dim
+
+
+def rank_transform(X):
+    """Average ranks (1..dim) of every row of the device tensor X (n, dim): float64 (n, dim)."""
+    device = require_cuda()
+    lib = _lib.load()
+    if X.dim() != 2 or X.dtype not in (torch.float32, torch.float64):
+        raise PhyloligoError("rank_transform expects a 2-D float32 / float64 device tensor")
+    X = X.contiguous()
+    n, dim = int(X.shape[0]), int(X.shape[1])
+    R = torch.empty((n, dim), dtype=torch.float64, device=device)
+    rc = lib.po_rank_transform(_ptr(X), PO_F32 if X.dtype == torch.float32 else PO_F64, n, dim, dim, _ptr(R), dim, _stream())
+    _lib.check(rc, "po_rank_transform")
+    return R
 
 
 def distance_block(metric, P, aux, dim, row0, row1, col0, col1, out, out_row0, out_col0, flags=0,

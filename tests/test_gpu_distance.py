@@ -320,3 +320,16 @@ def test_full_size_matrix_properties(metric, n, dim):
         blk = torch.empty((300, n), dtype=torch.float32, device="cuda")
         engine.distance_block(metric, P, aux, d, r0, r0 + 300, 0, n, blk, r0, 0)
         assert torch.equal(torch.nan_to_num(blk, nan=-7.0), torch.nan_to_num(M[r0:r0 + 300], nan=-7.0))
+
+
+@pytest.mark.parametrize("dim", [1, 2, 7, 256, 1000, 4096])
+def test_rank_transform_matches_scipy_rankdata(dim):
+    import scipy.stats as sst
+    rng = np.random.default_rng(dim)
+    X = rng.integers(0, 9, size=(37, dim)).astype(np.float64)
+    X[:10] = rng.random((10, dim))
+    X[11] = 3.0
+    for dtype in (np.float64, np.float32):
+        got = engine.rank_transform(torch.from_numpy(X.astype(dtype)).cuda()).cpu().numpy()
+        want = np.vstack([sst.rankdata(r.astype(dtype), method="average") for r in X])
+        assert np.array_equal(got, want)
