@@ -149,3 +149,24 @@ def test_host_binding_is_a_no_op_without_topology():
     assert engine.bind_host_to_gpu_node(0) is None or isinstance(engine.bind_host_to_gpu_node(0), int)
     if not torch.cuda.is_available():
         assert os.sched_getaffinity(0) == before
+
+
+def test_kount_window_table_matches_the_oracle_windows():
+    """kount.window_table (vectorised) against the restated make_genome_chunk rules (reference
+    bin/Kount.py:343-407, pinned by tests/golden/kount_golden.json) over many lengths and parameters."""
+    from oracle import kount_oracle as ko
+    from phyloligo_b200 import kount
+
+    rng = np.random.default_rng(4)
+    for w, t in ((5000, 500), (300, 50), (250, 100), (1000, 999), (64, 1), (7, 3), (100, 100), (101, 50)):
+        lengths = sorted(set([0, 1, w - 1, w, w + 1, 20 * t - 1, 20 * t, 20 * t + 1, w + t, w + 20 * t]
+                             + [int(v) for v in rng.integers(0, 30 * max(w, t), 25)]))
+        lengths = [n for n in lengths if n >= 0 and n < 400_000]
+        records = [("c%d" % i, "A" * n) for i, n in enumerate(lengths)]
+        want = ko.make_windows(records, w, t)
+        rec, start, size, dstart, dstop = kount.window_table(np.array(lengths), w, t)
+        assert rec.shape[0] == len(want)
+        got = [("c%d" % r, int(a), int(b), int(m)) for r, a, b, m in zip(rec, dstart, dstop, size)]
+        assert got == [(sid, a, b, len(s)) for sid, a, b, s in want], (w, t)
+        # window start offsets: every window string is the record's slice [start, start + size)
+        assert all(int(s0) + int(m) <= lengths[int(r)] for r, s0, m in zip(rec, start, size))
