@@ -2,9 +2,9 @@
 """Sliding-window mode (Kount.py) on one GPU: windows/s and window-bases/s on a synthetic assembly,
 next to the Python restatement of the reference timed on a sample of the same windows.
 
-    python tools/bench_kount.py --contigs 2000 --mean-len 100000 -w 5000 -t 500 -d JSD"""
+    python tests/tools/bench_kount.py --contigs 2000 --mean-len 100000 -w 5000 -t 500 -d JSD"""
 import argparse, json, os, sys, tempfile, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from phyloligo_b200 import kount, synth, _lib
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Max relative error of the GPU JSD matrix against the float64 oracle on a few profile sets (run on the GPU box)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from phyloligo_b200 import engine, synth
 from oracle import coracle

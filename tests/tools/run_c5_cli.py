@@ -3,12 +3,12 @@
 streaming its rows into the shared file.  The full configuration (1 M contigs, a 4 TB matrix) does
 not fit any scratch disk here; --contigs sets the size actually run.
 
-    python tools/run_c5_cli.py --gpus 8 --contigs 60000 --workdir /dev/shm
+    python tests/tools/run_c5_cli.py --gpus 8 --contigs 60000 --workdir /dev/shm
 
 Prints one JSON line: wall time of the torchrun command, stage times reported by rank 0, and a check
 of the file (exact zero diagonal, symmetry and sampled entries against the float64 oracle)."""
 import argparse, json, os, subprocess, sys, tempfile, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 
