@@ -9,10 +9,11 @@
 //   * centring: x' = x - mean profile (a Euclidean distance is translation invariant);
 //     ||x'|| is then of the order of the distances themselves instead of ~1/sqrt(D);
 //   * x' * 2^14 is split into two float16 values hi + lo (22 significant bits); the tensor
-//     cores form hi.hi, hi.lo and lo.hi in three separate float32 accumulators in TMEM
-//     (the dropped lo.lo term is 2^-22 relative) and the epilogue adds hh + (hl + lh): every
-//     accumulator sees the same products in the same order for (r, c) and (c, r), so the
-//     matrix is bitwise symmetric whichever tile computes an entry;
+//     cores form hi.hi in one float32 accumulator in TMEM and hi.lo + lo.hi in a second one
+//     (the dropped lo.lo term is 2^-22 relative) and the epilogue adds them.  The order of the
+//     two cross MMAs is mirrored below the diagonal and diagonal groups copy their lower half
+//     from their upper half, so (r, c) and (c, r) are the same float32 sums and the matrix is
+//     bitwise symmetric whichever tile computes an entry;
 //   * the row norms are float64 sums over the very same hi + lo values, and the epilogue
 //     evaluates n_a + n_b - 2 dot in float64.
 //   * entries whose Gram form cancels by more than 2^8 (n_a + n_b > 256 d^2: near-duplicate
@@ -26,11 +27,12 @@
 // Layout.  po_prepare_profiles writes, for every group of 128 profiles and every block of
 // 64 dimensions, the hi block and the lo block (16 KB each) in the canonical no-swizzle
 // K-major UMMA shared-memory layout: 8x16-byte core matrices, 128 B apart along the rows
-// and 2 KB apart along K.  A CTA computes one 128 x 128 tile: one thread streams the four
-// blocks of a K block (A hi/lo, B hi/lo) with cp.async.bulk into a 3-stage ring, one thread
-// issues 12 tcgen05.mma (128x128x16, kind::f16) per stage and commits them to the stage's
-// "empty" barrier, and after the last commit all four warps read the accumulator with
-// tcgen05.ld (one row per thread), finish the distance and store the tile (and its mirror).
+// and 2 KB apart along K.  A CTA of 16 warps computes one tile (Eucl: 128 x 256, two column
+// groups sharing the row operand; SC: 128 x 128): one thread streams the operand blocks of a K
+// stage with cp.async.bulk into a shared-memory ring, one thread issues the tcgen05.mma
+// (128x128x16, kind::f16) of the stage and commits them to the stage's "empty" barrier, and after
+// the last commit all warps read the accumulators with tcgen05.ld, finish the distances and
+// store the tile (and its mirror) with coalesced stores.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "po_common.cuh"
@@ -41,10 +43,8 @@ namespace po {
 constexpr int GT = 128;                 // tile edge (M = N = 128)
 constexpr int GK = 64;                  // K elements per block (4 MMAs of K = 16)
 constexpr int GBLOCK_BYTES = GT * GK * 2;     // one operand block: 16 KB
-constexpr int GSTAGE_BYTES = 4 * GBLOCK_BYTES;  // A hi, A lo, B hi, B lo
-constexpr int GSTAGES = 3;
 constexpr int GTHREADS = 512;             // 16 warps: two of them also drive the pipeline, all 16 share the epilogue
-constexpr int GRASTER = 16;             // tile columns per rasterisation chunk
+constexpr int GRASTER = 16;             // 128-column groups per rasterisation chunk
 constexpr float GSCALE = 16384.0f;      // 2^14
 constexpr double GUNSCALE = 1.0 / (16384.0 * 16384.0);
 
@@ -69,9 +69,9 @@ int64_t gram_prepared_bytes(int64_t n, int64_t dim) {
 // centred; average ranks for ties -- the scipy.stats.spearmanr step of phylodist.SC, reference
 // core/phylodist.py:82-85), rho = r'_a . r'_b / sqrt(|r'_a|^2 |r'_b|^2).  r' is split into two
 // integer digits r' = 64 h + l, l in [-32, 31], both exact in float16; the tensor cores form
-// h.h', (h.l' + l.h') and l.l' in the three TMEM accumulators.  Every product and every partial sum
+// h.h', h.l', l.h' and l.l' in four TMEM accumulators.  Every product and every partial sum
 // is an integer below 2^24 for dim <= 4096, so the float32 accumulators are exact and the epilogue
-// rebuilds the integer dot product 4096 hh + 64 x + ll: the result is bit for bit that of the
+// rebuilds the integer dot product 4096 hh + 64 (hl + lh) + ll: the result is bit for bit that of the
 // CUDA-core kernel (po_distance.cu, K_SC).  PO_SC_CUDA_CORES=1 selects that kernel instead.
 bool sc_use_gram(int metric, int64_t dim) {
     if (metric != PO_SC) return false;
@@ -330,13 +330,33 @@ struct GramParams {
 };
 
 
-// Epilogue of one tile.  Warp w owns TMEM lanes 32 (w & 3) .. +31 (the rows a warp may read) and the
-// 32 columns 32 (w >> 2) .. +31, in two chunks of 16.  Mirrored entries are stored straight from the
-// registers (lanes = consecutive rows = consecutive addresses of the mirrored row); the direct
-// entries go through a 32 x 33 shared-memory transpose so that a warp stores 128 contiguous bytes of
-// one output row per instruction.  The operand ring is free by now.  Addresses are one 64-bit base
-// per thread plus small offsets; INTERIOR tiles carry no per-entry bounds tests.
-template <typename OUT_T, int MODE, bool INTERIOR>
+// Tile geometry per mode.  Eucl: the CTA computes 128 rows x 256 columns (two 128-column groups that
+// share the row operand in shared memory: a quarter less operand traffic out of L2, which is what
+// bounds the kernel at large K), with two accumulators per group -- hi.hi and hi.lo + lo.hi -- so
+// that both groups fit the 512 TMEM columns; the K stage is 32 wide (48 KB) in a 4-deep ring.
+// SC: 128 x 128, four exact integer accumulators (hh, hl, lh, ll), 64-wide stages (64 KB) in a 3-deep ring.
+template <int MODE> struct GramCfg;
+#ifndef GRAM_EUCL_NB
+#define GRAM_EUCL_NB 2
+#endif
+template <> struct GramCfg<GM_EUCL> {
+    static constexpr int NB = GRAM_EUCL_NB, KS = (GRAM_EUCL_NB == 2 ? 32 : 64), STAGES = (GRAM_EUCL_NB == 2 ? 4 : 3), GROUP_COLS = 256;
+};
+template <> struct GramCfg<GM_SC>   { static constexpr int NB = 1, KS = 64, STAGES = 3, GROUP_COLS = 384; };
+
+// Epilogue of one 128 x 128 group of a tile.  Warp w owns TMEM lanes 32 (w & 3) .. +31 (the rows a
+// warp may read) and the 32 columns 32 (w >> 2) .. +31, in two chunks of 16.  Mirrored entries are
+// stored straight from the registers (lanes = consecutive rows = consecutive addresses of the
+// mirrored row); the direct entries go through a shared-memory transpose so that a warp stores 128
+// contiguous bytes of one output row per instruction.  The operand ring is free by now.  Addresses
+// are one 64-bit base per thread plus small offsets; INTERIOR groups carry no per-entry bounds tests.
+//
+// Eucl, diagonal group (row_base == col_base): with the cross terms hi.lo and lo.hi sharing one
+// accumulator, (r, c) and (c, r) of the same group see their products in a different order.  The
+// entries on and right of the diagonal are authoritative; the ones left of it are read back
+// transposed from a 128 x 129 shared-memory copy of the group (DIAG).  Groups wholly below the
+// diagonal get the same effect from the MMA issue order (see the kernel).
+template <typename OUT_T, int MODE, bool INTERIOR, bool DIAG>
 __device__ __forceinline__ void gram_epilogue(const GramParams& p, unsigned tmem, int64_t row_base, int64_t col_base,
                                               const double* s_nb, unsigned char* gsmem) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -345,20 +365,24 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, unsigned tmem
     const int64_t grow = row_base + r;
     const bool row_ok = INTERIOR || (grow >= p.row0 && grow < p.row1);
     const double na = (INTERIOR || grow < p.n) ? p.aux[grow] : 0.0;
-    const bool do_mirror = (p.flags & PO_FLAG_MIRROR) && row_base + GT <= col_base;
-    const bool diag_tile = row_base == col_base;
+    const bool do_mirror = !DIAG && (p.flags & PO_FLAG_MIRROR) && row_base + GT <= col_base;
     const int64_t ldx32 = (int64_t)p.nkb * GK;
-    OUT_T* tbuf = reinterpret_cast<OUT_T*>(gsmem) + (size_t)warp * (32 * 33);
+    constexpr int TP = DIAG ? (GT + 1) : 33;  // pitch of the staging buffer in elements
+    OUT_T* tbuf = DIAG ? reinterpret_cast<OUT_T*>(gsmem) + (size_t)r * TP + cq * 32
+                       : reinterpret_cast<OUT_T*>(gsmem) + (size_t)warp * (32 * 33) + (size_t)lane * TP;
     // mirrored entry (c, r) of this thread's row r and tile column 0
     OUT_T* mir_col0 = reinterpret_cast<OUT_T*>(p.mir) + (col_base - p.mir_row0) * p.ld_mir + (grow - p.mir_col0);
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
         const int c0 = cq * 32 + half * 16;
-        uint32_t vh[16], vx[16], vy[16];
+        uint32_t vh[16], vx[16], vy[16], vz[16];
         const unsigned ta = tmem + ((unsigned)(lq * 32) << 16) + (unsigned)c0;
         g_tmem_ld16(ta, vh);
         g_tmem_ld16(ta + GT, vx);
-        g_tmem_ld16(ta + 2 * GT, vy);
+        if (MODE == GM_SC) {
+            g_tmem_ld16(ta + 2 * GT, vy);
+            g_tmem_ld16(ta + 3 * GT, vz);
+        }
         g_tmem_wait_ld();
         OUT_T val[16];
         unsigned cancel = 0u;  // columns of this chunk whose Gram form cancelled too much
@@ -367,19 +391,22 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, unsigned tmem
             const double nb = s_nb[c0 + j];
             if (MODE == GM_SC) {
                 // exact integer dot product of the centred doubled ranks, then 1 - rho as K_SC does
-                const long long t = 4096ll * (long long)__uint_as_float(vh[j]) + 64ll * (long long)__uint_as_float(vx[j]) +
-                                    (long long)__uint_as_float(vy[j]);
+                const long long t = 4096ll * (long long)__uint_as_float(vh[j]) +
+                                    64ll * ((long long)__uint_as_float(vx[j]) + (long long)__uint_as_float(vy[j])) +
+                                    (long long)__uint_as_float(vz[j]);
                 const double den = sqrt(na * nb);
                 const double v = (den == 0.0) ? __longlong_as_double(0x7FF8000000000000ll)  // scipy: NaN for a constant row
                                               : 1.0 - (double)t / den;
                 val[j] = (OUT_T)v;
                 continue;
             }
-            const float dot = __uint_as_float(vh[j]) + (__uint_as_float(vx[j]) + __uint_as_float(vy[j]));
+            const float dot = __uint_as_float(vh[j]) + __uint_as_float(vx[j]);
             const double nsum = na + nb;
             double d2 = nsum - 2.0 * (double)dot;
-            const bool on_diag = diag_tile && r == c0 + j;
-            const bool inside = INTERIOR || (row_ok && col_base + c0 + j >= p.col0 && col_base + c0 + j < p.col1);
+            const bool on_diag = DIAG && r == c0 + j;
+            // a diagonal group recomputes for all its entries: the ones left of the diagonal are copies
+            const bool inside = DIAG ? (grow < p.n && col_base + c0 + j < p.n)
+                                     : (INTERIOR || (row_ok && col_base + c0 + j >= p.col0 && col_base + c0 + j < p.col1));
             if (inside && !on_diag && d2 * 256.0 < nsum) cancel |= 1u << j;
             d2 = (d2 > 0.0 ? d2 : 0.0) * GUNSCALE;
             if (sizeof(OUT_T) == 8) val[j] = (OUT_T)sqrt(d2);
@@ -426,17 +453,28 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, unsigned tmem
             }
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) tbuf[lane * 33 + half * 16 + j] = val[j];
+        for (int j = 0; j < 16; ++j) tbuf[half * 16 + j] = val[j];
     }
-    __syncwarp();
+    if (DIAG) __syncthreads();  // every warp reads other warps' rows of the group below
+    else __syncwarp();
     {
-        const int64_t gcol = col_base + cq * 32 + lane;
+        const int c = cq * 32 + lane;  // column of the group this lane stores
+        const int64_t gcol = col_base + c;
         const bool col_ok = INTERIOR || (gcol >= p.col0 && gcol < p.col1);
         const int64_t gr0 = row_base + lq * 32;
         OUT_T* op = reinterpret_cast<OUT_T*>(p.out) + (gr0 - p.out_row0) * p.ld_out + (gcol - p.out_col0);
+        const OUT_T* dt = reinterpret_cast<const OUT_T*>(gsmem);
+        const OUT_T* wb = reinterpret_cast<const OUT_T*>(gsmem) + (size_t)warp * (32 * 33);
 #pragma unroll 8
         for (int rr = 0; rr < 32; ++rr) {
-            if (INTERIOR || (col_ok && gr0 + rr >= p.row0 && gr0 + rr < p.row1)) *op = tbuf[rr * 33 + lane];
+            OUT_T v;
+            if (DIAG) {
+                const int rw = lq * 32 + rr;
+                v = (c >= rw) ? dt[(size_t)rw * TP + c] : dt[(size_t)c * TP + rw];
+            } else {
+                v = wb[rr * 33 + lane];
+            }
+            if (INTERIOR || (col_ok && gr0 + rr >= p.row0 && gr0 + rr < p.row1)) *op = v;
             op += p.ld_out;
         }
     }
@@ -444,34 +482,50 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, unsigned tmem
 
 template <typename OUT_T, int MODE>
 __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams p) {
+    using Cfg = GramCfg<MODE>;
+    constexpr int NB = Cfg::NB, KS = Cfg::KS, NSTAGE = Cfg::STAGES;
+    constexpr int SUB_BYTES = GT * KS * 2;               // one operand (hi or lo) of one 128-profile group per stage
+    constexpr int STAGE_BYTES = (1 + NB) * 2 * SUB_BYTES;  // A hi, A lo, then B hi, B lo per group
+    constexpr int TILE_N = NB * GT;
     extern __shared__ __align__(1024) unsigned char gsmem[];
-    __shared__ __align__(8) unsigned long long bars[2 * GSTAGES + 1];
+    __shared__ __align__(8) unsigned long long bars[2 * NSTAGE + 1];
     __shared__ uint32_t s_tmem;
-    __shared__ double s_nb[GT];  // the tile columns' row constants (squared norms / rank sums)
+    __shared__ double s_nb[TILE_N];  // the tile columns' row constants (squared norms / rank sums)
     // rasterisation: chunks of GRASTER tile columns, all tile rows inside a chunk, so that the
     // chunk's column operands (GRASTER x 2 MB at 4096 dimensions) stay in L2 while the rows stream
-    const int64_t per_chunk = p.tiles_r * GRASTER;
+    constexpr int RASTER = GRASTER / NB;  // the chunk stays GRASTER groups (2048 profiles) wide
+    const int64_t per_chunk = p.tiles_r * RASTER;
     const int64_t chunk = (int64_t)blockIdx.x / per_chunk;
     const int64_t rem = (int64_t)blockIdx.x - chunk * per_chunk;
-    const int64_t gw = min((int64_t)GRASTER, p.tiles_c - chunk * GRASTER);
+    const int64_t gw = min((int64_t)RASTER, p.tiles_c - chunk * RASTER);
     const int64_t row_base = p.tile_row0 + (rem / gw) * GT;
-    const int64_t col_base = p.tile_col0 + (chunk * GRASTER + rem % gw) * GT;
-    if ((p.flags & PO_FLAG_SKIP_LOWER) && col_base + GT <= row_base) return;
+    const int64_t col_base = p.tile_col0 + (chunk * RASTER + rem % gw) * TILE_N;
+    const int64_t npad = (p.n + GT - 1) / GT * GT;
+    // which 128-column groups of the tile have anything to do
+    bool act[NB];
+    bool any = false;
+#pragma unroll
+    for (int g = 0; g < NB; ++g) {
+        const int64_t cb = col_base + (int64_t)g * GT;
+        act[g] = cb < npad && cb < p.col1 && cb + GT > p.col0 && !((p.flags & PO_FLAG_SKIP_LOWER) && cb + GT <= row_base);
+        any = any || act[g];
+    }
+    if (!any) return;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned smem0 = g_smem_u32(gsmem);
-    const unsigned full0 = g_smem_u32(&bars[0]), empty0 = g_smem_u32(&bars[GSTAGES]), accum = g_smem_u32(&bars[2 * GSTAGES]);
+    const unsigned full0 = g_smem_u32(&bars[0]), empty0 = g_smem_u32(&bars[NSTAGE]), accum = g_smem_u32(&bars[2 * NSTAGE]);
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < GSTAGES; ++s) {
+        for (int s = 0; s < NSTAGE; ++s) {
             g_mbar_init(full0 + 8 * s, 1);
             g_mbar_init(empty0 + 8 * s, 1);
         }
         g_mbar_init(accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {  // one warp allocates the TMEM columns (three 128 x 128 float32 accumulators)
+    if (warp == 0) {  // one warp allocates all 512 TMEM columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(&s_tmem)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -481,74 +535,131 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
     const unsigned tmem = s_tmem;
 
     const int nkb = p.nkb;
-    const unsigned char* gA = p.P + (size_t)(row_base / GT) * nkb * 2 * GBLOCK_BYTES;
-    const unsigned char* gB = p.P + (size_t)(col_base / GT) * nkb * 2 * GBLOCK_BYTES;
+    const int nks = nkb * (GK / KS);  // K stages of the tile
+    // operand (grp, stage kq, hi/lo): the KS-wide slice of the 64-wide block, chunk-major inside the block
+    auto g_operand = [&](int64_t grp, int kq, int hl) -> const unsigned char* {
+        const int kb = (kq * KS) / GK;
+        const int chunk0 = ((kq * KS) % GK) / 8;
+        return p.P + (((size_t)grp * nkb + kb) * 2 + hl) * GBLOCK_BYTES + (size_t)chunk0 * 2048;
+    };
+    const int64_t grp_a = row_base / GT, grp_b0 = col_base / GT;
 
     if (warp == 0 && lane == 0) {
-        // ===== producer: four bulk copies per K block =====
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % GSTAGES;
-            g_mbar_wait(empty0 + 8 * s, (unsigned)(((kb / GSTAGES) & 1) ^ 1));
-            const unsigned dst = smem0 + s * GSTAGE_BYTES;
-            g_mbar_expect_tx(full0 + 8 * s, GSTAGE_BYTES);
-            g_bulk_g2s(dst, gA + (size_t)kb * 2 * GBLOCK_BYTES, 2 * GBLOCK_BYTES, full0 + 8 * s);
-            g_bulk_g2s(dst + 2 * GBLOCK_BYTES, gB + (size_t)kb * 2 * GBLOCK_BYTES, 2 * GBLOCK_BYTES, full0 + 8 * s);
+        // ===== producer: two bulk copies for the rows and two per active column group =====
+        unsigned stage_bytes = 2 * SUB_BYTES;
+#pragma unroll
+        for (int g = 0; g < NB; ++g) stage_bytes += act[g] ? 2 * SUB_BYTES : 0;
+        for (int kq = 0; kq < nks; ++kq) {
+            const int s = kq % NSTAGE;
+            g_mbar_wait(empty0 + 8 * s, (unsigned)(((kq / NSTAGE) & 1) ^ 1));
+            const unsigned dst = smem0 + s * STAGE_BYTES;
+            g_mbar_expect_tx(full0 + 8 * s, stage_bytes);
+            g_bulk_g2s(dst, g_operand(grp_a, kq, 0), SUB_BYTES, full0 + 8 * s);
+            g_bulk_g2s(dst + SUB_BYTES, g_operand(grp_a, kq, 1), SUB_BYTES, full0 + 8 * s);
+#pragma unroll
+            for (int g = 0; g < NB; ++g) {
+                if (!act[g]) continue;
+                g_bulk_g2s(dst + (2 + 2 * g) * SUB_BYTES, g_operand(grp_b0 + g, kq, 0), SUB_BYTES, full0 + 8 * s);
+                g_bulk_g2s(dst + (3 + 2 * g) * SUB_BYTES, g_operand(grp_b0 + g, kq, 1), SUB_BYTES, full0 + 8 * s);
+            }
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         // instruction descriptor: D float32, A/B float16 K-major, N = 128, M = 128
         const unsigned idesc = (1u << 4) | ((unsigned)(GT >> 3) << 17) | ((unsigned)(GT >> 4) << 24);
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % GSTAGES;
-            g_mbar_wait(full0 + 8 * s, (unsigned)((kb / GSTAGES) & 1));
+        for (int kq = 0; kq < nks; ++kq) {
+            const int s = kq % NSTAGE;
+            g_mbar_wait(full0 + 8 * s, (unsigned)((kq / NSTAGE) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const unsigned a_hi = smem0 + s * GSTAGE_BYTES, a_lo = a_hi + GBLOCK_BYTES;
-            const unsigned b_hi = a_hi + 2 * GBLOCK_BYTES, b_lo = b_hi + GBLOCK_BYTES;
+            const unsigned a_hi = smem0 + s * STAGE_BYTES, a_lo = a_hi + SUB_BYTES;
 #pragma unroll
-            for (int ks = 0; ks < GK / 16; ++ks) {
+            for (int ks = 0; ks < KS / 16; ++ks) {
                 const unsigned koff = ks * 2 * 2048;  // two 8-element chunks per MMA
                 const uint64_t dah = g_smem_desc(a_hi + koff), dal = g_smem_desc(a_lo + koff);
-                const uint64_t dbh = g_smem_desc(b_hi + koff), dbl = g_smem_desc(b_lo + koff);
-                const unsigned acc = (kb > 0 || ks > 0) ? 1u : 0u;
-                g_mma_f16(tmem, dah, dbh, idesc, acc);
-                if (MODE == GM_EUCL) {
+                const unsigned acc = (kq > 0 || ks > 0) ? 1u : 0u;
+                // Two MMAs into the same accumulator back to back serialise in the tensor pipe, so the
+                // issue order keeps them apart: SC has four accumulators (hh, hl, lh, ll: distance 4);
+                // Eucl issues cross(a) of both groups, hh of group 0, cross(b) of both groups, hh of
+                // group 1 (distance 3 for the cross accumulators, 6 for hh).
+                if (MODE == GM_SC) {
+                    const unsigned b_hi = a_hi + 2 * SUB_BYTES, b_lo = b_hi + SUB_BYTES;
+                    const uint64_t dbh = g_smem_desc(b_hi + koff), dbl = g_smem_desc(b_lo + koff);
+                    g_mma_f16(tmem, dah, dbh, idesc, acc);
                     g_mma_f16(tmem + GT, dah, dbl, idesc, acc);
                     g_mma_f16(tmem + 2 * GT, dal, dbh, idesc, acc);
-                } else {  // integer digits: the cross terms share an accumulator, lo.lo is kept
-                    g_mma_f16(tmem + GT, dah, dbl, idesc, acc);
-                    g_mma_f16(tmem + GT, dal, dbh, idesc, 1u);
-                    g_mma_f16(tmem + 2 * GT, dal, dbl, idesc, acc);
+                    g_mma_f16(tmem + 3 * GT, dal, dbl, idesc, acc);
+                } else {
+                    uint64_t dbh[NB], dbl[NB];
+                    bool upper[NB];
+#pragma unroll
+                    for (int g = 0; g < NB; ++g) {
+                        const unsigned b_hi = a_hi + (2 + 2 * g) * SUB_BYTES;
+                        dbh[g] = g_smem_desc(b_hi + koff);
+                        dbl[g] = g_smem_desc(b_hi + SUB_BYTES + koff);
+                        // hi.lo + lo.hi share an accumulator.  A group below the diagonal issues them in the
+                        // order its mirror image above the diagonal does, so that (r, c) and (c, r) are the
+                        // same float32 sum whichever group computes them.
+                        upper[g] = col_base + (int64_t)g * GT >= row_base;
+                    }
+#pragma unroll
+                    for (int g = 0; g < NB; ++g)
+                        if (act[g]) g_mma_f16(tmem + g * Cfg::GROUP_COLS + GT, upper[g] ? dah : dal, upper[g] ? dbl[g] : dbh[g], idesc, acc);
+                    if (act[0]) g_mma_f16(tmem, dah, dbh[0], idesc, acc);
+#pragma unroll
+                    for (int g = 0; g < NB; ++g)
+                        if (act[g]) g_mma_f16(tmem + g * Cfg::GROUP_COLS + GT, upper[g] ? dal : dah, upper[g] ? dbh[g] : dbl[g], idesc, 1u);
+                    if (NB > 1 && act[NB - 1]) g_mma_f16(tmem + (NB - 1) * Cfg::GROUP_COLS, dah, dbh[NB - 1], idesc, acc);
                 }
             }
             g_mma_commit(empty0 + 8 * s);  // the stage is free once these MMAs have read it
         }
-        g_mma_commit(accum);  // accumulator complete
+        g_mma_commit(accum);  // accumulators complete
     }
     __syncwarp();
 
-    // ===== epilogue (gram_epilogue): all 16 warps =====
-    if (tid < GT) {
+    // ===== epilogue (gram_epilogue): all 16 warps, one 128-column group after the other =====
+    if (tid < TILE_N) {
         const int64_t gc = col_base + tid;
         s_nb[tid] = (gc < p.n) ? p.aux[gc] : 0.0;
     }
     __syncthreads();
     g_mbar_wait(accum, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // tiles wholly inside the requested block (all but the ragged edges) skip the per-entry bounds tests
-    const bool interior = row_base >= p.row0 && row_base + GT <= p.row1 && col_base >= p.col0 && col_base + GT <= p.col1;
-    if (interior)
-        gram_epilogue<OUT_T, MODE, true>(p, tmem, row_base, col_base, s_nb, gsmem);
-    else
-        gram_epilogue<OUT_T, MODE, false>(p, tmem, row_base, col_base, s_nb, gsmem);
+#pragma unroll
+    for (int g = 0; g < NB; ++g) {
+        if (!act[g]) continue;
+        const int64_t cb = col_base + (int64_t)g * GT;
+        const unsigned tg = tmem + (unsigned)(g * Cfg::GROUP_COLS);
+        // groups wholly inside the requested block (all but the ragged edges) skip the per-entry bounds tests
+        const bool interior = row_base >= p.row0 && row_base + GT <= p.row1 && cb >= p.col0 && cb + GT <= p.col1;
+        if (MODE == GM_EUCL && cb == row_base)
+            gram_epilogue<OUT_T, MODE, false, true>(p, tg, row_base, cb, s_nb + g * GT, gsmem);
+        else if (interior)
+            gram_epilogue<OUT_T, MODE, true, false>(p, tg, row_base, cb, s_nb + g * GT, gsmem);
+        else
+            gram_epilogue<OUT_T, MODE, false, false>(p, tg, row_base, cb, s_nb + g * GT, gsmem);
+        if (NB > 1) __syncthreads();  // the staging buffers are reused by the next group
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }
 
 template <typename OUT_T, int MODE>
-static int launch_gram_t(const GramParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
+static int launch_gram_t(GramParams p, int64_t row1, int64_t col1, cudaStream_t stream) {
+    using Cfg = GramCfg<MODE>;
+    const int64_t tile_n = (int64_t)Cfg::NB * GT;
+    p.tile_col0 = p.col0 / tile_n * tile_n;
+    const int64_t tr = (row1 - p.tile_row0 + GT - 1) / GT, tc = (col1 - p.tile_col0 + tile_n - 1) / tile_n;
+    if (tr * tc > 0x7FFFFFFFll) {
+        set_error("block too large: %lld x %lld tiles", (long long)tr, (long long)tc);
+        return PO_ERR_UNSUPPORTED;
+    }
+    p.tiles_r = tr;
+    p.tiles_c = tc;
+    const size_t smem = (size_t)Cfg::STAGES * (1 + Cfg::NB) * 2 * GT * Cfg::KS * 2 + 1024;
     PO_CUDA_CHECK(cudaFuncSetAttribute(gram_tile_kernel<OUT_T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gram_tile_kernel<OUT_T, MODE><<<grid, GTHREADS, smem, stream>>>(p);
+    gram_tile_kernel<OUT_T, MODE><<<dim3((unsigned)(tr * tc), 1, 1), GTHREADS, smem, stream>>>(p);
     return PO_OK;
 }
 
@@ -570,27 +681,17 @@ int launch_gram(int metric, const void* d_P, const double* d_aux, int64_t n, int
     p.n = n;
     p.row0 = row0; p.row1 = row1; p.col0 = col0; p.col1 = col1;
     p.tile_row0 = row0 / GT * GT;
-    p.tile_col0 = col0 / GT * GT;
     p.out = d_out; p.ld_out = ld_out; p.out_row0 = out_row0; p.out_col0 = out_col0;
     p.mir = d_mir; p.ld_mir = ld_mir; p.mir_row0 = mir_row0; p.mir_col0 = mir_col0;
     p.flags = flags;
-    const int64_t tr = (row1 - p.tile_row0 + GT - 1) / GT, tc = (col1 - p.tile_col0 + GT - 1) / GT;
-    if (tr * tc > 0x7FFFFFFFll) {
-        set_error("block too large: %lld x %lld tiles", (long long)tr, (long long)tc);
-        return PO_ERR_UNSUPPORTED;
-    }
-    p.tiles_r = tr;
-    p.tiles_c = tc;
-    const size_t smem = (size_t)GSTAGES * GSTAGE_BYTES + 1024;
-    dim3 grid((unsigned)(tr * tc), 1, 1);
     LaunchTimer tm(1, stream);
     int rc;
     if (metric == PO_SC)
-        rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_SC>(p, grid, smem, stream)
-                                 : launch_gram_t<double, GM_SC>(p, grid, smem, stream);
+        rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_SC>(p, row1, col1, stream)
+                                 : launch_gram_t<double, GM_SC>(p, row1, col1, stream);
     else
-        rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_EUCL>(p, grid, smem, stream)
-                                 : launch_gram_t<double, GM_EUCL>(p, grid, smem, stream);
+        rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_EUCL>(p, row1, col1, stream)
+                                 : launch_gram_t<double, GM_EUCL>(p, row1, col1, stream);
     if (rc != PO_OK) return rc;
     count_launch(1);
     PO_LAUNCH_CHECK("gram_tile_kernel");
