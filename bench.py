@@ -327,7 +327,17 @@ def run_ours(args):
         avail = 0
     host_result = None
     if not args.ring_sink and host_bytes * world < 0.5 * avail:
-        host_result = torch.empty((host_rows_n, n_contigs), dtype=torch.float32).pin_memory()
+        try:
+            host_result = torch.empty((host_rows_n, n_contigs), dtype=torch.float32).pin_memory()
+        except RuntimeError as exc:  # page-locking refused (cgroup / ulimit): fall back to the panel ring
+            print("bench: cannot pin %.1f GB of host memory (%s); using the ring sink" % (host_bytes / 1e9, exc),
+                  file=sys.stderr)
+            host_result = None
+    if world > 1:  # every rank must take the same path (the barriers inside BlockRows.compute are collective)
+        flag = torch.tensor([1 if host_result is not None else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            host_result = None
     pin_ring = None
     if host_result is None:
         pin_ring = [torch.empty((panel, n_contigs), dtype=torch.float32).pin_memory() for _ in range(2)]
