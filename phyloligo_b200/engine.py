@@ -234,23 +234,31 @@ class PeerRows:
         lib = _lib.load()
         handle = (C.c_ubyte * 64)()
         off = C.c_int64()
-        _lib.check(lib.po_ipc_export(_ptr(local_rows), handle, C.byref(off)), "po_ipc_export")
-        mine = (bytes(handle), int(off.value), torch.cuda.current_device())
+        mine = None
+        if lib.po_ipc_export(_ptr(local_rows), handle, C.byref(off)) == 0:
+            mine = (bytes(handle), int(off.value), torch.cuda.current_device())
         everyone = [None] * world
-        dist.all_gather_object(everyone, mine)
+        dist.all_gather_object(everyone, mine)  # every rank reaches this, whether its export worked or not
+        if any(e is None for e in everyone):
+            raise PhyloligoError("peer memory: po_ipc_export failed on rank(s) %s"
+                                 % [r for r, e in enumerate(everyone) if e is None])
         self.local = local_rows
         self.rank = rank
         self._bases = {}
         self._addr = {}
-        for r, (h, offset, dev) in enumerate(everyone):
-            if r == rank:
-                self._addr[r] = local_rows.data_ptr()
-                continue
-            base = C.c_void_p()
-            buf = (C.c_ubyte * 64).from_buffer_copy(h)
-            _lib.check(lib.po_ipc_open(buf, C.byref(base)), "po_ipc_open")
-            self._bases[r] = base
-            self._addr[r] = int(base.value) + offset
+        try:
+            for r, (h, offset, dev) in enumerate(everyone):
+                if r == rank:
+                    self._addr[r] = local_rows.data_ptr()
+                    continue
+                base = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(h)
+                _lib.check(lib.po_ipc_open(buf, C.byref(base)), "po_ipc_open")
+                self._bases[r] = base
+                self._addr[r] = int(base.value) + offset
+        except PhyloligoError:
+            self.close()
+            raise
 
     def address(self, rank):
         return self._addr[rank]

@@ -64,8 +64,22 @@ class BlockRows:
         self.staging = None
         self._copy_stream = None
         if world > 1 and self.exchange == "peer":
-            self.peers = engine.PeerRows(self.matrix, rank, world)
-        elif world > 1:
+            # mapping can be refused (no peer access between two GPUs, an allocator that hands out
+            # unexportable memory): then every rank falls back to the NCCL exchange together
+            try:
+                self.peers = engine.PeerRows(self.matrix, rank, world)
+                ok = 1
+            except engine.PhyloligoError as exc:
+                self.peers, ok = None, 0
+                self._peer_error = str(exc)
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if self.peers is not None:
+                    self.peers.close()
+                    self.peers = None
+                self.exchange = "nccl"
+        if world > 1 and self.peers is None:
             self.staging = {}
             for i in self.my_ranges:
                 a, b = self.ranges[i]

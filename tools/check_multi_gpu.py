@@ -31,8 +31,9 @@ for exchange in ("peer", "nccl"):
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
+            used = job.exchange if job.exchange == exchange else "%s->%s" % (exchange, job.exchange)
             print("%-5s %-8s n=%d world=%d rows identical to the single-GPU matrix: %s"
-                  % (exchange, metric, n, world, bool(flag.item())), flush=True)
+                  % (used, metric, n, world, bool(flag.item())), flush=True)
         job.close()
         assert ok, "rank %d rows differ (%s, %s)" % (rank, exchange, metric)
 dist.destroy_process_group()
