@@ -27,6 +27,7 @@ struct LaunchTimer {
         if (_e != cudaSuccess) {                                                         \
             po::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
                           __FILE__, __LINE__);                                           \
+            (void)cudaGetLastError(); /* reported here: do not leave it for the next launch check */ \
             return PO_ERR_CUDA;                                                          \
         }                                                                                \
     } while (0)
