@@ -54,12 +54,15 @@ enum po_metric {
 enum po_dtype { PO_F32 = 0, PO_F64 = 1 };
 
 /* flags of po_distance_block */
-#define PO_FLAG_SKIP_LOWER 1u /* skip 64x64 tiles that lie wholly below the diagonal          */
-#define PO_FLAG_MIRROR     2u /* tiles wholly above the diagonal are also written transposed */
+#define PO_FLAG_SKIP_LOWER 1u /* skip the kernel tiles that lie wholly below the diagonal       */
+#define PO_FLAG_MIRROR     2u /* tiles wholly above the diagonal are also written transposed  */
 
 #define PO_MAX_PATTERN 32 /* longest spaced pattern (window width) */
 #define PO_MAX_K       10 /* most '1's in a pattern (4^10 bins)     */
-#define PO_TILE        64 /* distance tile edge                      */
+#define PO_TILE        64 /* tile edge of the CUDA-core distance kernels                       */
+#define PO_TILE_ALIGN 128 /* largest tile granule of any distance kernel (32x64 JSD, 64x64 CUDA-core
+                             metrics, 128x128 groups on the tensor cores): block boundaries that are
+                             multiples of it never split a tile between two calls */
 
 const char* po_version(void);
 const char* po_last_error(void);

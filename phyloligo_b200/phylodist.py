@@ -1,6 +1,7 @@
 """Pair-level distance functions with the reference's names and argument meaning
 (reference phylopackage/core/phylodist.py:36-85), executed by the CUDA tile kernel.
 
+    KL(a, b)    sum a ln(a/b), NaN / Inf terms zeroed (1-D)     core/phylodist.py:18-34
     Eucl(a, b)  sqrt(sum (a-b)^2)                              core/phylodist.py:36-41
     JSD(a, b)   Jensen-Shannon divergence in nats               core/phylodist.py:43-68
                 (1-D x 1-D -> scalar; 2-D x 2-D -> matrix whose rows index `b`)
@@ -39,6 +40,18 @@ def _pair_or_cross(a, b, metric):
     if a.ndim == 1 and b.ndim == 1:
         return engine.pair_distance(a, b, metric)
     return _cross(a, b, metric)
+
+
+def KL(a, b):
+    """Kullback-Leibler divergence of two profiles in nats, terms that are NaN or infinite (a zero
+    on either side) dropped -- the 1-D branch of the reference (core/phylodist.py:20-24).  Its 2-D
+    branch calls an un-imported helper (NameError) and is never reached from phyloligo.py."""
+    from . import kount
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.ndim != 1 or b.ndim != 1:
+        raise engine.PhyloligoError("KL takes two 1-D profiles (the reference's 2-D branch raises NameError)")
+    return kount.KL(a, b)
 
 
 def Eucl(a, b):

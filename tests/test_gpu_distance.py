@@ -150,6 +150,11 @@ def test_pair_api_and_block_rows():
     assert phylodist.BC(X[0], X[1]) == pytest.approx(po.BC(X[0], X[1]), rel=2e-6)
     assert phylodist.KT(X[0], X[1]) == pytest.approx(po.KT(X[0], X[1]), abs=1e-12)
     assert phylodist.SC(X[0], X[1]) == pytest.approx(po.SC(X[0], X[1]), abs=1e-12)
+    assert phylodist.KL(X[0], X[1]) == pytest.approx(po.KL(X[0], X[1]), rel=1e-12)
+    z = X[2].copy()
+    z[::3] = 0.0  # zeros on one side: those terms are dropped, as posdef_check_value does
+    assert phylodist.KL(z, X[1]) == pytest.approx(po.KL(z, X[1]), rel=1e-12)
+    assert phylodist.KL(X[1], z) == pytest.approx(po.KL(X[1], z), rel=1e-12)
     # 2-D x 2-D JSD: rows index the second argument (core/phylodist.py:58-66)
     X32 = X.astype(np.float32)
     got = phylodist.JSD(X32, X32[10:31])
