@@ -170,3 +170,36 @@ def test_kount_window_table_matches_the_oracle_windows():
         assert got == [(sid, a, b, len(s)) for sid, a, b, s in want], (w, t)
         # window start offsets: every window string is the record's slice [start, start + size)
         assert all(int(s0) + int(m) <= lengths[int(r)] for r, s0, m in zip(rec, start, size))
+
+
+def test_hdf5_attach_lets_other_processes_fill_the_dataset(tmp_path):
+    """The multi-GPU command line: rank 0 creates the one-dataset file, every rank attaches to the
+    data region and writes its rows; the file reads back as one matrix."""
+    path = os.path.join(tmp_path, "d.h5")
+    io_formats.Hdf5DatasetWriter(path, "distances", (7, 5), np.float32).close()
+    shape, dtype, addr = io_formats.dataset_location(path, "distances")
+    assert shape == (7, 5) and np.dtype(dtype) == np.float32 and addr % 8 == 0
+    want = np.arange(35, dtype=np.float32).reshape(7, 5)
+    for rows in ((0, 3), (3, 7)):  # two "ranks"
+        with io_formats.Hdf5DatasetWriter.attach(path, "distances") as w:
+            w.write_rows(rows[0], want[rows[0]:rows[1]])
+    assert np.array_equal(io_formats.read_hdf5(path, "distances"), want)
+    assert os.path.getsize(path) == addr + 35 * 4  # the data region ends the file (superblock EOF address)
+
+
+def test_kount_assembly_layout_matches_the_fasta_reader(tmp_path):
+    """kount.Assembly (host side only): record ids as Biopython's record.id, sequences without line
+    breaks, one separator between records."""
+    from oracle import kount_oracle as ko
+    from phyloligo_b200 import kount
+
+    path = os.path.join(tmp_path, "a.fasta")
+    with open(path, "wb") as fh:
+        fh.write(b"junk before the first record\n>c1 first contig\nACGT\nacgtNN\n\n>c2\n>c3|x desc\r\nAC GT\r\nTT\r\n>last\nGATTACA")
+    asm = kount.Assembly(path)
+    want = ko.read_records(path)
+    assert asm.ids == [w[0] for w in want] == ["c1", "c2", "c3|x", "last"]
+    assert [asm.sequence(i) for i in range(asm.n)] == [w[1] for w in want]
+    assert list(asm.lengths) == [10, 0, 6, 7]
+    for i in range(asm.n):  # every record is followed by exactly one separator
+        assert asm.text[int(asm.offsets[i] + asm.lengths[i])] == 10
