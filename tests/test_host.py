@@ -203,3 +203,31 @@ def test_kount_assembly_layout_matches_the_fasta_reader(tmp_path):
     assert list(asm.lengths) == [10, 0, 6, 7]
     for i in range(asm.n):  # every record is followed by exactly one separator
         assert asm.text[int(asm.offsets[i] + asm.lengths[i])] == 10
+
+
+def test_savetxt_digits_are_correctly_rounded_everywhere(tmp_path):
+    """The printf-free '%.18e' path of po_savetxt_host (128-bit scaled arithmetic, snprintf only when a
+    rounding boundary cannot be decided) against Python's own formatting: random bit patterns over the
+    whole double range (subnormals included), powers of two and ten, exact ties at the 19th digit."""
+    rng = np.random.default_rng(1)
+    vals = rng.integers(0, 2 ** 63, size=120_000, dtype=np.int64).astype(np.uint64).view(np.float64)
+    vals = vals[np.isfinite(vals)]
+    vals[::2] *= -1.0
+    spec = [0.0, -0.0, 1.0, 0.5, 0.1, 1 / 3, 1e22, 1e23, 9.999999999999999e22, 5e-324, 2.2250738585072014e-308,
+            2.225073858507201e-308, 1.7976931348623157e308, 1e-20, 1e19, 9.5, 99.5, 4.35, 3.0517578125e-05]
+    spec += [float(2.0 ** i) for i in range(-1074, 1024, 7)] + [float(10 ** i) for i in range(23)]
+    spec += [1.0 / float(10 ** i) for i in range(1, 23)]
+    spec += [(2 * i + 1) / 2.0 ** 20 for i in range(0, 3000, 7)]          # 20 significant digits ending in 5: ties
+    spec += [(2 * i + 1) / 2.0 ** 40 for i in range(10 ** 6, 10 ** 6 + 300)]
+    spec += [float(i) / 1024 for i in range(1, 300)]
+    allv = np.concatenate([vals, np.array(spec, dtype=np.float64)])
+    path = os.path.join(tmp_path, "v.txt")
+    io_formats.savetxt(path, allv.reshape(-1, 1), threads=3)
+    got = open(path).read().split("\n")[:-1]
+    assert len(got) == allv.shape[0]
+    bad = [(float(x), g) for x, g in zip(allv, got) if g != "%.18e" % float(x)]
+    assert not bad, bad[:5]
+    f32 = rng.random(50_000).astype(np.float32) * np.float32(10.0) ** rng.integers(-30, 30, 50_000).astype(np.float32)
+    io_formats.savetxt(path, f32.reshape(-1, 1))
+    got = open(path).read().split("\n")[:-1]
+    assert all(g == "%.18e" % float(x) for x, g in zip(f32, got))
