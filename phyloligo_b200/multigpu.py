@@ -112,7 +112,7 @@ class BlockRows:
         row's tiles; the part left of the diagonal block is written by the other ranks and leaves
         after the closing barrier.  Returns `matrix`."""
         n = self.n
-        compute_stream = torch.cuda.current_stream()
+        compute_stream = torch.cuda.current_stream() if host_rows is not None else None
         if host_rows is not None:
             if tuple(host_rows.shape) != tuple(self.matrix.shape) or not host_rows.is_pinned():
                 raise RuntimeError("host_rows must be a pinned tensor of the shape of BlockRows.matrix")

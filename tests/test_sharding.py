@@ -86,3 +86,53 @@ def test_range_offsets_stack_the_owned_ranges(n, world):
         for i in sharding.owned_ranges(rg, rank, world):
             assert off[i] == expect
             expect += rg[i][1] - rg[i][0]
+
+
+def _block_rows_worker(rank, world, port, n, dim):
+    """multigpu.BlockRows end to end under gloo: the tile launches are replaced by a CPU stand-in that
+    fills `out` and the mirror target exactly as po_distance_block_ex addresses them."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from phyloligo_b200 import engine, multigpu
+        from phyloligo_b200._lib import FLAG_MIRROR, FLAG_SKIP_LOWER
+
+        rng = np.random.default_rng(5)
+        X = rng.dirichlet(np.ones(dim), size=n)
+        full = torch.from_numpy(po.pairwise_np(X, "Eucl"))
+        calls = []
+
+        def fake_block(metric, P, aux, d, row0, row1, col0, col1, out, out_row0, out_col0, flags=0, mirror=None,
+                       mirror_row0=0, mirror_col0=0, mirror_ld=None):
+            calls.append((row0, row1, col0, col1))
+            blk = full[row0:row1, col0:col1]
+            if flags & FLAG_SKIP_LOWER:  # diagonal block: upper triangle computed, mirrored in place
+                assert (row0, row1) == (col0, col1) and mirror is None
+            out[row0 - out_row0:row1 - out_row0, col0 - out_col0:col1 - out_col0] = blk
+            if (flags & FLAG_MIRROR) and mirror is not None:
+                assert isinstance(mirror, torch.Tensor)  # the NCCL-exchange path stages locally
+                mirror[col0 - mirror_row0:col1 - mirror_row0, row0 - mirror_col0:row1 - mirror_col0] = blk.T
+
+        engine.distance_block, keep = fake_block, engine.distance_block
+        try:
+            job = multigpu.BlockRows(n, torch.float64, rank, world, exchange="nccl", device=torch.device("cpu"))
+            job.matrix.fill_(float("nan"))
+            job.compute("Eucl", None, None, dim)
+        finally:
+            engine.distance_block = keep
+        for i, rows in job.out_rows.items():
+            a, b = job.ranges[i]
+            assert torch.equal(rows, full[a:b]), "rank %d block row %d" % (rank, i)
+        # every unordered pair of blocks is computed by exactly one rank: upper-triangle area only
+        mine = sum((r1 - r0) * (c1 - c0) for r0, r1, c0, c1 in calls)
+        diag = sum((r1 - r0) ** 2 for r0, r1, c0, c1 in calls if (r0, r1) == (c0, c1))
+        assert mine - diag + (diag + sum(r1 - r0 for r0, r1, c0, c1 in calls if (r0, r1) == (c0, c1))) // 2 == job.upper_area()
+        job.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 700), (3, 1000)])
+def test_block_rows_orchestration_gloo(world, n):
+    mp.spawn(_block_rows_worker, args=(world, _free_port(), n, 12), nprocs=world, join=True)
