@@ -231,3 +231,29 @@ def test_savetxt_digits_are_correctly_rounded_everywhere(tmp_path):
     io_formats.savetxt(path, f32.reshape(-1, 1))
     got = open(path).read().split("\n")[:-1]
     assert all(g == "%.18e" % float(x) for x, g in zip(f32, got))
+
+
+def test_fasta_index_fuzz_against_the_reader(tmp_path):
+    """Random line soups (headers anywhere, '>' inside lines, blank lines, CRLF, blanks inside lines, no final
+    newline, text before the first header) : po_fasta_index_host yields the records SeqIO.parse would."""
+    from hypothesis import given, settings, strategies as st
+
+    line = st.one_of(
+        st.text(alphabet="ACGTNacgtn >", min_size=0, max_size=30),
+        st.text(alphabet="ACGT", min_size=0, max_size=5).map(lambda s: ">" + s + " desc"),
+        st.just(""), st.just(">"), st.just(">>x"))
+    path = os.path.join(tmp_path, "fuzz.fa")
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(line, min_size=0, max_size=25), st.sampled_from(["\n", "\r\n"]), st.booleans())
+    def run(lines, eol, final_eol):
+        text = eol.join(lines) + (eol if final_eol and lines else "")
+        raw = text.encode()
+        with open(path, "wb") as fh:
+            fh.write(raw)
+        want = list(po.read_fasta(path))
+        begin, end = engine.fasta_index(raw, threads=2)
+        got = [bytes(raw[b:e]).decode().replace("\n", "").replace("\r", "").replace(" ", "") for b, e in zip(begin, end)]
+        assert got == want
+
+    run()
