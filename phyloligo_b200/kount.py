@@ -288,9 +288,11 @@ def sliding_windows_distances(genome, mcp_comparison, mth_dist="JSD", pattern="1
     asm = _assembly(genome)
     rec, start, size, dstart, dstop = window_table(asm.lengths, windows_size, windows_step)
     dist = window_distance_vector(asm, rec, start, size, mcp_comparison, mth_dist, str(pattern), strand, n_max)
+    ids = asm.ids
     for c0 in range(0, rec.shape[0], YIELD_WINDOWS):
         c1 = min(rec.shape[0], c0 + YIELD_WINDOWS)
-        yield [[asm.ids[int(rec[k])], int(dstart[k]), int(dstop[k]), float(dist[k])] for k in range(c0, c1)]
+        yield [[ids[r], a, b, d] for r, a, b, d in zip(rec[c0:c1].tolist(), dstart[c0:c1].tolist(),
+                                                       dstop[c0:c1].tolist(), dist[c0:c1].tolist())]
 
 
 def vector_to_matrix(profile):
