@@ -259,6 +259,41 @@ int po_copy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_p
 int po_savetxt_host(const char* path, const void* h_data, int64_t rows, int64_t cols, int64_t ld,
                     int dtype, int threads);
 
+/*
+ * The host end of the output path.  The reference's --large workers assign their block row into
+ * the caller's mapping of the output file (output[s] = ..., bin/phyloligo.py:202-222 into the
+ * np.memmap of :413-425, or the 'distances' dataset of the HDF5 file, :471-478).  Here block
+ * rows leave the device by DMA (po_copy2d_async), and these calls make the caller's mapping a
+ * DMA target or move finished panels into it with host threads.  All pointers are HOST pointers;
+ * `threads` <= 0 picks the hardware concurrency.
+ *   po_host_prefault      instantiate the pages of [h_ptr, h_ptr + bytes) for writing (parallel
+ *                         madvise(MADV_POPULATE_WRITE); touches every page on kernels without it)
+ *   po_host_register      page-lock an existing mapping (cudaHostRegister, portable) so that
+ *                         po_copy2d_async DMAs straight into it; fails with PO_ERR_CUDA when the
+ *                         kernel refuses to pin the pages (file systems with dirty tracking)
+ *   po_host_unregister    undo it (before munmap)
+ *   po_host_copy2d        strided block copy host -> host on `threads` threads (pinned panel ->
+ *                         mapping of the output file)
+ *   po_host_pwrite2d      the same through pwrite(fd, ...) at file_offset with row pitch file_pitch
+ *                         (no page faults, no mapping needed)
+ *   po_host_pread         read `bytes` bytes at file_offset of fd into h_dst with `threads` parallel
+ *                         pread calls: how the FASTA text reaches the pinned staging ring (the
+ *                         SeqIO.parse(genome, "fasta") reads of bin/phyloligo.py:869, 914, 959)
+ *   po_host_transpose_f32 h_dst[c * ld_dst + r] = h_src[r * ld_src + c], float32: the mirrored block
+ *                         of a block that has already arrived (the matrix is symmetric), so that only
+ *                         the part on and right of the diagonal needs to cross PCIe
+ */
+int po_host_prefault(void* h_ptr, int64_t bytes, int threads);
+int po_host_register(void* h_ptr, int64_t bytes);
+int po_host_unregister(void* h_ptr);
+int po_host_copy2d(void* h_dst, int64_t dst_pitch, const void* h_src, int64_t src_pitch, int64_t width,
+                   int64_t rows, int threads);
+int po_host_pwrite2d(int fd, int64_t file_offset, int64_t file_pitch, const void* h_src, int64_t src_pitch,
+                     int64_t width, int64_t rows, int threads);
+int po_host_pread(int fd, int64_t file_offset, void* h_dst, int64_t bytes, int threads);
+int po_host_transpose_f32(float* h_dst, int64_t ld_dst, const float* h_src, int64_t ld_src, int64_t rows,
+                          int64_t cols, int threads);
+
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t po_launch_count(void);
 

@@ -26,7 +26,9 @@ TILE = 128  # largest kernel tile edge: row panels and rank boundaries are multi
 EXPORTED = [
     "po_version", "po_last_error", "po_device_info", "po_pattern_info", "po_fasta_index_host",
     "po_profile_batch", "po_prepared_row_bytes", "po_prepared_bytes", "po_prepare_profiles", "po_rank_transform", "po_distance_block", "po_distance_block_ex",
-    "po_ipc_export", "po_ipc_open", "po_ipc_close", "po_savetxt_host", "po_copy2d_async", "po_window_count_byte", "po_window_distances", "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read", "po_microbench",
+    "po_ipc_export", "po_ipc_open", "po_ipc_close", "po_savetxt_host", "po_copy2d_async", "po_window_count_byte", "po_window_distances",
+    "po_host_prefault", "po_host_register", "po_host_unregister", "po_host_copy2d", "po_host_pwrite2d",
+    "po_host_pread", "po_host_transpose_f32", "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read", "po_microbench",
 ]
 
 
@@ -88,6 +90,20 @@ def load():
     lib.po_copy2d_async.restype = i32
     lib.po_savetxt_host.argtypes = [C.c_char_p, vp, i64, i64, i64, i32, i32]
     lib.po_savetxt_host.restype = i32
+    lib.po_host_prefault.argtypes = [vp, i64, i32]
+    lib.po_host_prefault.restype = i32
+    lib.po_host_register.argtypes = [vp, i64]
+    lib.po_host_register.restype = i32
+    lib.po_host_unregister.argtypes = [vp]
+    lib.po_host_unregister.restype = i32
+    lib.po_host_copy2d.argtypes = [vp, i64, vp, i64, i64, i64, i32]
+    lib.po_host_copy2d.restype = i32
+    lib.po_host_pwrite2d.argtypes = [i32, i64, i64, vp, i64, i64, i64, i32]
+    lib.po_host_pwrite2d.restype = i32
+    lib.po_host_pread.argtypes = [i32, i64, vp, i64, i32]
+    lib.po_host_pread.restype = i32
+    lib.po_host_transpose_f32.argtypes = [vp, i64, vp, i64, i64, i64, i32]
+    lib.po_host_transpose_f32.restype = i32
     lib.po_launch_count.restype = i64
     lib.po_timing_enable.argtypes = [i32]
     lib.po_timing_enable.restype = i32

@@ -81,23 +81,20 @@ struct Accum<K_BC> {  // sum|a-b|; the denominator sum|a+b| = sum a + sum b for 
 
 template <>
 struct Accum<K_SC> {  // exact integer dot product of centred doubled ranks
-    int c[4][4];
+    // The products go straight into 64-bit accumulators (one IMAD.WIDE per term): a centred doubled
+    // rank reaches dim - 1, so at dim = 16384 (k = 7) 32 products of correlated rows already exceed
+    // 2^31, and above dim = 46341 a single product does.  (64 <= dim <= 4096 runs on the tensor cores.)
     long long t[4][4];
     __device__ __forceinline__ void init() {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { c[i][j] = 0; t[i][j] = 0; }
+            for (int j = 0; j < 4; ++j) t[i][j] = 0;
     }
     __device__ __forceinline__ void term(int i, int j, float a, float b) {
-        c[i][j] += __float_as_int(a) * __float_as_int(b);
+        t[i][j] += (long long)__float_as_int(a) * (long long)__float_as_int(b);
     }
-    __device__ __forceinline__ void fold() {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { t[i][j] += (long long)c[i][j]; c[i][j] = 0; }
-    }
+    __device__ __forceinline__ void fold() {}
     __device__ __forceinline__ double result(int i, int j, double ssa, double ssb) const {
         const double den = sqrt(ssa * ssb);
         if (den == 0.0) return __longlong_as_double(0x7FF8000000000000ll);  // scipy: NaN for a constant row

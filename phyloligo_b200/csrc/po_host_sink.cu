@@ -1,0 +1,272 @@
+// Host side of the output path (no device code): where finished block rows of the distance
+// matrix land.
+//
+// The reference's --large workers write their block row straight into the caller's mapping:
+// output[s] = ... into an np.memmap of the N x N float32 file (bin/phyloligo.py:202-222,
+// 413-425) or into the data region of the HDF5 file (:471-478).  Here the block rows come off
+// the device by DMA, and the same mapping is the DMA target when the kernel lets us page-lock
+// it (po_host_register on a tmpfs / anonymous mapping); otherwise they go through a pinned
+// ring and a pool of host threads moves them (po_host_copy2d into the mapping, or
+// po_host_pwrite2d through the page cache, which never takes a page fault).  Fresh pages of
+// the output file are instantiated ahead of the copies by po_host_prefault.
+// po_host_transpose_f32 is the host half of "ship the upper triangle only": the part of the
+// matrix left of the diagonal is the transpose of what has already arrived.
+#include <errno.h>
+#include <fcntl.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <unistd.h>
+#include <xmmintrin.h>
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+#include "po_common.cuh"
+
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
+
+namespace po {
+
+static int pick_threads(int threads, int64_t work_bytes) {
+    if (threads <= 0) {
+        threads = (int)std::thread::hardware_concurrency();
+        if (threads <= 0) threads = 1;
+    }
+    if (threads > 256) threads = 256;
+    // below ~1 MB per thread the start-up of a thread costs more than it moves
+    const int64_t useful = work_bytes / (1 << 20) + 1;
+    if ((int64_t)threads > useful) threads = (int)useful;
+    return threads;
+}
+
+// run fn(t) for t in [0, threads) on `threads` host threads (the caller's thread is one of them)
+template <typename F>
+static void run_threads(int threads, F fn) {
+    if (threads <= 1) {
+        fn(0);
+        return;
+    }
+    std::vector<std::thread> pool;
+    pool.reserve((size_t)threads - 1);
+    for (int t = 1; t < threads; ++t) pool.emplace_back(fn, t);
+    fn(0);
+    for (auto& th : pool) th.join();
+}
+
+}  // namespace po
+
+using namespace po;
+
+extern "C" {
+
+int po_host_prefault(void* h_ptr, int64_t bytes, int threads) {
+    if (bytes < 0 || (bytes > 0 && !h_ptr)) {
+        set_error("po_host_prefault: bad arguments");
+        return PO_ERR_ARG;
+    }
+    if (bytes == 0) return PO_OK;
+    const long page = sysconf(_SC_PAGESIZE);
+    uintptr_t lo = (uintptr_t)h_ptr & ~(uintptr_t)(page - 1);
+    const uintptr_t hi = ((uintptr_t)h_ptr + (uintptr_t)bytes + page - 1) & ~(uintptr_t)(page - 1);
+    threads = pick_threads(threads, (int64_t)(hi - lo) / 16);
+    const uintptr_t span = hi - lo;
+    std::atomic<int> failed{0};
+    run_threads(threads, [&](int t) {
+        uintptr_t a = lo + (span / page * t / threads) * page;
+        const uintptr_t b = (t == threads - 1) ? hi : lo + (span / page * (t + 1) / threads) * page;
+        // 64 MB at a time: a populate call holds mmap_lock for reading throughout
+        const uintptr_t step = (uintptr_t)64 << 20;
+        bool use_madvise = true;
+        while (a < b) {
+            const uintptr_t e = std::min(b, a + step);
+            if (use_madvise && madvise((void*)a, e - a, MADV_POPULATE_WRITE) != 0) {
+                if (errno == EINVAL || errno == ENOSYS) {
+                    use_madvise = false;  // kernel older than 5.14: touch every page instead
+                } else {
+                    failed.store(errno);
+                    return;
+                }
+            }
+            if (!use_madvise) {
+                for (uintptr_t q = a; q < e; q += page) {
+                    volatile unsigned char* c = (volatile unsigned char*)q;
+                    *c = *c;
+                }
+            }
+            a = e;
+        }
+    });
+    if (failed.load()) {
+        set_error("po_host_prefault: madvise(MADV_POPULATE_WRITE) failed: %s", strerror(failed.load()));
+        return PO_ERR_ARG;
+    }
+    return PO_OK;
+}
+
+int po_host_register(void* h_ptr, int64_t bytes) {
+    if (!h_ptr || bytes <= 0) {
+        set_error("po_host_register: bad arguments");
+        return PO_ERR_ARG;
+    }
+    PO_CUDA_CHECK(cudaHostRegister(h_ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return PO_OK;
+}
+
+int po_host_unregister(void* h_ptr) {
+    if (!h_ptr) return PO_OK;
+    PO_CUDA_CHECK(cudaHostUnregister(h_ptr));
+    return PO_OK;
+}
+
+int po_host_copy2d(void* h_dst, int64_t dst_pitch, const void* h_src, int64_t src_pitch, int64_t width,
+                   int64_t rows, int threads) {
+    if (width < 0 || rows < 0 || dst_pitch < width || src_pitch < width) {
+        set_error("po_host_copy2d: bad geometry");
+        return PO_ERR_ARG;
+    }
+    if (width == 0 || rows == 0) return PO_OK;
+    if (!h_dst || !h_src) {
+        set_error("po_host_copy2d: NULL pointer");
+        return PO_ERR_ARG;
+    }
+    threads = pick_threads(threads, width * rows);
+    if ((int64_t)threads > rows) threads = (int)rows;
+    run_threads(threads, [&](int t) {
+        const int64_t r0 = rows * t / threads, r1 = rows * (t + 1) / threads;
+        if (dst_pitch == width && src_pitch == width) {
+            memcpy((char*)h_dst + r0 * width, (const char*)h_src + r0 * width, (size_t)((r1 - r0) * width));
+            return;
+        }
+        for (int64_t r = r0; r < r1; ++r)
+            memcpy((char*)h_dst + r * dst_pitch, (const char*)h_src + r * src_pitch, (size_t)width);
+    });
+    return PO_OK;
+}
+
+int po_host_pwrite2d(int fd, int64_t file_offset, int64_t file_pitch, const void* h_src, int64_t src_pitch,
+                     int64_t width, int64_t rows, int threads) {
+    if (fd < 0 || width < 0 || rows < 0 || file_pitch < width || src_pitch < width || file_offset < 0) {
+        set_error("po_host_pwrite2d: bad arguments");
+        return PO_ERR_ARG;
+    }
+    if (width == 0 || rows == 0) return PO_OK;
+    if (!h_src) {
+        set_error("po_host_pwrite2d: NULL pointer");
+        return PO_ERR_ARG;
+    }
+    threads = pick_threads(threads, width * rows);
+    if ((int64_t)threads > rows) threads = (int)rows;
+    std::atomic<int> failed{0};
+    run_threads(threads, [&](int t) {
+        const int64_t r0 = rows * t / threads, r1 = rows * (t + 1) / threads;
+        const bool dense = file_pitch == width && src_pitch == width;
+        const int64_t pieces = dense ? 1 : r1 - r0;
+        for (int64_t k = 0; k < pieces && !failed.load(std::memory_order_relaxed); ++k) {
+            const int64_t r = r0 + k;
+            const char* src = (const char*)h_src + r * src_pitch;
+            int64_t off = file_offset + r * file_pitch;
+            int64_t left = dense ? (r1 - r0) * width : width;
+            while (left > 0) {
+                const ssize_t w = pwrite(fd, src, (size_t)std::min<int64_t>(left, (int64_t)1 << 30), (off_t)off);
+                if (w < 0) {
+                    if (errno == EINTR) continue;
+                    failed.store(errno);
+                    return;
+                }
+                src += w;
+                off += w;
+                left -= w;
+            }
+        }
+    });
+    if (failed.load()) {
+        set_error("po_host_pwrite2d: pwrite failed: %s", strerror(failed.load()));
+        return PO_ERR_ARG;
+    }
+    return PO_OK;
+}
+
+int po_host_pread(int fd, int64_t file_offset, void* h_dst, int64_t bytes, int threads) {
+    if (fd < 0 || file_offset < 0 || bytes < 0 || (bytes > 0 && !h_dst)) {
+        set_error("po_host_pread: bad arguments");
+        return PO_ERR_ARG;
+    }
+    if (bytes == 0) return PO_OK;
+    threads = pick_threads(threads, bytes);
+    std::atomic<int> failed{0};
+    run_threads(threads, [&](int t) {
+        int64_t a = bytes * t / threads;
+        const int64_t b = bytes * (t + 1) / threads;
+        while (a < b) {
+            const ssize_t r = pread(fd, (char*)h_dst + a, (size_t)(b - a), (off_t)(file_offset + a));
+            if (r < 0) {
+                if (errno == EINTR) continue;
+                failed.store(errno);
+                return;
+            }
+            if (r == 0) {  // shorter file than announced
+                failed.store(EIO);
+                return;
+            }
+            a += r;
+        }
+    });
+    if (failed.load()) {
+        set_error("po_host_pread: pread failed: %s", strerror(failed.load()));
+        return PO_ERR_ARG;
+    }
+    return PO_OK;
+}
+
+int po_host_transpose_f32(float* h_dst, int64_t ld_dst, const float* h_src, int64_t ld_src, int64_t rows,
+                          int64_t cols, int threads) {
+    if (rows < 0 || cols < 0 || ld_src < cols || ld_dst < rows) {
+        set_error("po_host_transpose_f32: bad geometry");
+        return PO_ERR_ARG;
+    }
+    if (rows == 0 || cols == 0) return PO_OK;
+    if (!h_dst || !h_src) {
+        set_error("po_host_transpose_f32: NULL pointer");
+        return PO_ERR_ARG;
+    }
+    // dst[c * ld_dst + r] = src[r * ld_src + c].  Tiles of 64 x 64 (16 KB in, 16 KB out: both in L1/L2),
+    // 4 x 4 register transposes inside; threads split the destination rows (= source columns) so that
+    // every thread writes whole cache lines of its own.
+    constexpr int64_t T = 64;
+    const int64_t ctiles = (cols + T - 1) / T;
+    threads = pick_threads(threads, rows * cols * 4);
+    if ((int64_t)threads > ctiles) threads = (int)ctiles;
+    run_threads(threads, [&](int t) {
+        const int64_t ct0 = ctiles * t / threads, ct1 = ctiles * (t + 1) / threads;
+        for (int64_t ct = ct0; ct < ct1; ++ct) {
+            const int64_t c0 = ct * T, c1 = std::min(cols, c0 + T);
+            for (int64_t r0 = 0; r0 < rows; r0 += T) {
+                const int64_t r1 = std::min(rows, r0 + T);
+                int64_t r = r0;
+                for (; r + 4 <= r1; r += 4) {
+                    int64_t c = c0;
+                    for (; c + 4 <= c1; c += 4) {
+                        __m128 a0 = _mm_loadu_ps(h_src + (r + 0) * ld_src + c);
+                        __m128 a1 = _mm_loadu_ps(h_src + (r + 1) * ld_src + c);
+                        __m128 a2 = _mm_loadu_ps(h_src + (r + 2) * ld_src + c);
+                        __m128 a3 = _mm_loadu_ps(h_src + (r + 3) * ld_src + c);
+                        _MM_TRANSPOSE4_PS(a0, a1, a2, a3);
+                        _mm_storeu_ps(h_dst + (c + 0) * ld_dst + r, a0);
+                        _mm_storeu_ps(h_dst + (c + 1) * ld_dst + r, a1);
+                        _mm_storeu_ps(h_dst + (c + 2) * ld_dst + r, a2);
+                        _mm_storeu_ps(h_dst + (c + 3) * ld_dst + r, a3);
+                    }
+                    for (; c < c1; ++c)
+                        for (int64_t rr = r; rr < r + 4; ++rr) h_dst[c * ld_dst + rr] = h_src[rr * ld_src + c];
+                }
+                for (; r < r1; ++r)
+                    for (int64_t c = c0; c < c1; ++c) h_dst[c * ld_dst + r] = h_src[r * ld_src + c];
+            }
+        }
+    });
+    return PO_OK;
+}
+
+}  // extern "C"

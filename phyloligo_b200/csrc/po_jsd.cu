@@ -404,20 +404,14 @@ int launch_jsd(const void* d_P, int64_t n, int64_t dim, int64_t row0, int64_t ro
     p.tiles_r = tr;
     p.tiles_c = tc;
     const size_t smem = (size_t)JSTAGES * JSTAGE_BYTES;
-    static bool attr_set[2] = {false, false};
     dim3 grid((unsigned)(tr * tc), 1, 1);
     LaunchTimer tm(1, stream);
+    // the opt-in is per device: set it on every launch (a process may drive several GPUs)
     if (out_dtype == PO_F32) {
-        if (!attr_set[0]) {
-            PO_CUDA_CHECK(cudaFuncSetAttribute(jsd_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set[0] = true;
-        }
+        PO_CUDA_CHECK(cudaFuncSetAttribute(jsd_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         jsd_tile_kernel<float><<<grid, JTHREADS, smem, stream>>>(p);
     } else {
-        if (!attr_set[1]) {
-            PO_CUDA_CHECK(cudaFuncSetAttribute(jsd_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set[1] = true;
-        }
+        PO_CUDA_CHECK(cudaFuncSetAttribute(jsd_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         jsd_tile_kernel<double><<<grid, JTHREADS, smem, stream>>>(p);
     }
     count_launch(1);

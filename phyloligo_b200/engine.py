@@ -103,6 +103,44 @@ def text_to_device(text, device=None, non_blocking=False):
     return dst
 
 
+def file_to_device(path, byte_lo=0, byte_hi=None, device=None, slot_bytes=32 << 20, threads=4):
+    """Bytes [byte_lo, byte_hi) of a file straight to the device, padded like text_to_device: parallel
+    pread (po_host_pread) into a two-slot pinned ring, each slot leaving by asynchronous H2D while the
+    other is being read.  Nothing the size of the file is page-locked or copied on the host (a
+    pageable np.fromfile of a 2 GB assembly plus its staged copy costs more than profiling it)."""
+    import os
+    device = device or require_cuda()
+    lib = _lib.load()
+    size = os.path.getsize(path)
+    byte_hi = size if byte_hi is None else min(int(byte_hi), size)
+    byte_lo = int(byte_lo)
+    n = max(0, byte_hi - byte_lo)
+    dst = torch.empty(n + 64, dtype=torch.uint8, device=device)
+    dst[n:].fill_(10)
+    if n == 0:
+        return dst
+    slot_bytes = int(min(slot_bytes, max(1 << 20, n)))
+    ring = [torch.empty(slot_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    events = [None, None]
+    fd = os.open(path, os.O_RDONLY)
+    try:
+        for k, off in enumerate(range(0, n, slot_bytes)):
+            m = min(slot_bytes, n - off)
+            slot = k & 1
+            if events[slot] is not None:
+                events[slot].synchronize()
+            _lib.check(lib.po_host_pread(fd, byte_lo + off, C.c_void_p(ring[slot].data_ptr()), m, threads), "po_host_pread")
+            dst[off:off + m].copy_(ring[slot][:m], non_blocking=True)
+            events[slot] = torch.cuda.Event()
+            events[slot].record()
+    finally:
+        os.close(fd)
+    for ev in events:
+        if ev is not None:
+            ev.synchronize()  # the ring is released on return
+    return dst
+
+
 def profile_device(d_text, d_begin, d_end, pattern, strand, want=("counts", "totals", "freq64")):
     """Launch po_profile_batch on device tensors; returns a dict of device tensors."""
     device = require_cuda()
@@ -171,6 +209,12 @@ def prepare(X, metric):
     n, dim = int(X.shape[0]), int(X.shape[1])
     total = lib.po_prepared_bytes(METRICS[metric], n, dim)
     _lib.check(total, "po_prepared_bytes")
+    free, _ = torch.cuda.mem_get_info()
+    if total > free:
+        hint = (" (KT keeps two bit planes over the dim(dim-1)/2 element pairs of every profile: %.1f MB per "
+                "profile at dim = %d)" % (total / max(1, n) / 1e6, dim)) if metric == "KT" else ""
+        raise PhyloligoError("%s: the prepared operands of %d profiles of dimension %d need %.1f GB, %.1f GB of "
+                             "device memory are free%s" % (metric, n, dim, total / 1e9, free / 1e9, hint))
     # a 2-D view with one row per profile keeps n visible to the callers; the buffer
     # itself is the opaque operand layout of the library (JSD pads it to 64-profile groups)
     words = total // 4

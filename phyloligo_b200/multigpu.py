@@ -103,28 +103,47 @@ class BlockRows:
     def upper_area(self):
         return sharding.upper_area(self.ranges, self.rank, self.world, self.n)
 
-    def compute(self, metric, P, aux, dim, host_rows=None):
+    def compute(self, metric, P, aux, dim, host_rows=None, ship=None):
         """Launch this rank's tiles; on return (in stream order) `matrix` holds its complete rows.
 
         With `host_rows` (a pinned [rows_owned x n] tensor) the rows also go to the host: the part of
         a block row from its diagonal block rightwards is written by this rank only, so it leaves on
         the copy stream as soon as that block row's launches are done, overlapping the next block
         row's tiles; the part left of the diagonal block is written by the other ranks and leaves
-        after the closing barrier.  Returns `matrix`."""
+        after the closing barrier.  `ship(block, row0, col0)` instead hands every such finished
+        device block (a view of `matrix`, with the matrix coordinates of its corner) to the caller in
+        the same order -- the command line's file sink (hostsink.RowShipper).  Returns `matrix`."""
         n = self.n
-        compute_stream = torch.cuda.current_stream() if host_rows is not None else None
         if host_rows is not None:
             if tuple(host_rows.shape) != tuple(self.matrix.shape) or not host_rows.is_pinned():
                 raise RuntimeError("host_rows must be a pinned tensor of the shape of BlockRows.matrix")
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream()
+            compute_stream = torch.cuda.current_stream()
+
+            def ship(block, row0, col0, _host=host_rows, _cs=compute_stream):  # noqa: F811
+                i = next(k for k in self.my_ranges if self.ranges[k][0] <= row0 < self.ranges[k][1])
+                off = self.offsets[i] + (row0 - self.ranges[i][0])
+                ready = torch.cuda.Event()
+                ready.record(_cs)
+                self._copy_stream.wait_event(ready)
+                engine.copy2d(_host[off:off + block.shape[0], col0:col0 + block.shape[1]], block, self._copy_stream)
+
+        def ship_part(i, right):
+            a, b = self.ranges[i]
+            rows = self.out_rows[i]
+            if right:
+                ship(rows[:, a:], a, a)
+            elif a > 0:
+                ship(rows[:, :a], a, 0)
+
         if self.peers is not None:
             self._device_barrier()  # the consumers of the previous result are done with the rows
         for k, i in enumerate(self.my_ranges):
             a, b = self.ranges[i]
             rows = self.out_rows[i]
-            if host_rows is not None and k > 0:
-                self._ship(host_rows, self.my_ranges[k - 1], compute_stream, right=True)
+            if ship is not None and k > 0:
+                ship_part(self.my_ranges[k - 1], right=True)
             engine.distance_block(metric, P, aux, dim, a, b, a, b, rows, a, 0, FLAG_SKIP_LOWER | FLAG_MIRROR)
             if b >= n:
                 continue
@@ -143,27 +162,15 @@ class BlockRows:
                 addr = base + self.offsets[q] * n * self.esize
                 engine.distance_block(metric, P, aux, dim, a, b, aq, bq, rows, a, 0, FLAG_MIRROR,
                                       mirror=addr, mirror_row0=aq, mirror_col0=0, mirror_ld=n)
-        if host_rows is not None and self.my_ranges:
-            self._ship(host_rows, self.my_ranges[-1], compute_stream, right=True)
+        if ship is not None and self.my_ranges:
+            ship_part(self.my_ranges[-1], right=True)
         if self.peers is not None:
             self._device_barrier()
         elif self.world > 1:
             sharding.exchange_transposed(self.staging, self.ranges, self.rank, self.world, self.out_rows)
-        if host_rows is not None:
+        if ship is not None:
             for i in self.my_ranges:
-                self._ship(host_rows, i, compute_stream, right=False)
-            compute_stream.wait_stream(self._copy_stream)
+                ship_part(i, right=False)
+        if host_rows is not None:
+            torch.cuda.current_stream().wait_stream(self._copy_stream)
         return self.matrix
-
-    def _ship(self, host_rows, i, compute_stream, right):
-        """Copy block row i to the host on the copy stream: its columns from the diagonal block on
-        (`right`) or the ones left of it, once everything launched so far on the compute stream is done."""
-        a, b = self.ranges[i]
-        off = self.offsets[i]
-        ready = torch.cuda.Event()
-        ready.record(compute_stream)
-        self._copy_stream.wait_event(ready)
-        if right:
-            engine.copy2d(host_rows[off:off + (b - a), a:], self.matrix[off:off + (b - a), a:], self._copy_stream)
-        else:
-            engine.copy2d(host_rows[off:off + (b - a), :a], self.matrix[off:off + (b - a), :a], self._copy_stream)

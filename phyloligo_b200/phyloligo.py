@@ -28,10 +28,11 @@ import tempfile
 import numpy as np
 import torch
 
-from . import engine, io_formats, phylodist
-from ._lib import PhyloligoError, METRICS, TILE
+from . import engine, hostsink, io_formats, phylodist
+from ._lib import PhyloligoError, METRICS, TILE, FLAG_MIRROR, FLAG_SKIP_LOWER
 
-PANEL_ROWS = None  # rows per streamed panel; None = engine.auto_panel_rows (about 256 MB per pinned buffer)
+PANEL_ROWS = None  # rows per computed panel of the streamed outputs; None = 4096
+RESIDENT_FRACTION = 0.6  # the matrix (or a rank's rows of it) stays on the device when it fits in this share of the free HBM
 
 
 def remove_folder(folder):
@@ -175,20 +176,43 @@ def _check_metric(metric):
 # ---------------------------------------------------------------------------
 # frequencies
 # ---------------------------------------------------------------------------
-def _read_genome(genome):
-    return np.fromfile(genome, dtype=np.uint8)
+_GENOME_INDEX = {}  # abspath -> (size, mtime_ns, begin, end): main() indexes the file while the CUDA context comes up
+
+
+def _map_genome(genome):
+    """The FASTA file mapped read-only (uint8 array; nothing is read until it is touched)."""
+    if os.path.getsize(genome) == 0:
+        return np.zeros(0, np.uint8)
+    return np.memmap(genome, dtype=np.uint8, mode="r")
+
+
+def _genome_index(genome, threads=0):
+    """(begin, end) of every record of the file (engine.fasta_index over the mapping), cached."""
+    key = os.path.abspath(genome)
+    st = os.stat(genome)
+    hit = _GENOME_INDEX.get(key)
+    if hit is not None and hit[0] == st.st_size and hit[1] == st.st_mtime_ns:
+        return hit[2], hit[3]
+    begin, end = engine.fasta_index(_map_genome(genome), threads=threads)
+    _GENOME_INDEX.clear()
+    _GENOME_INDEX[key] = (st.st_size, st.st_mtime_ns, begin, end)
+    return begin, end
 
 
 def _profile_file(genome, pattern, strand, want):
     rank, world = ranks()
     if world > 1:
         return _profile_file_sharded(genome, pattern, strand, want, rank, world)
-    text = _read_genome(genome)
-    begin, end = engine.fasta_index(text)
+    begin, end = _genome_index(genome)
     if begin.shape[0] == 0:
         _, _, dim = engine._lib.pattern_info(str(pattern))
         return None, 0, dim
-    res = engine.profile_text(text, str(pattern), strand, want, begin, end)
+    device = engine.require_cuda()
+    lo, hi = int(begin[0]), int(end[-1])
+    d_text = engine.file_to_device(genome, lo, hi, device)  # header of the first record and before: not needed
+    d_begin = torch.from_numpy(begin - lo).to(device)
+    d_end = torch.from_numpy(end - lo).to(device)
+    res = engine.profile_device(d_text, d_begin, d_end, str(pattern), strand, want)
     return res, int(begin.shape[0]), None
 
 
@@ -199,8 +223,7 @@ def _profile_file_sharded(genome, pattern, strand, want, rank, world):
     import torch.distributed as dist
     from . import sharding
     (key,) = want
-    text = np.memmap(genome, dtype=np.uint8, mode="r") if os.path.getsize(genome) else np.zeros(0, np.uint8)
-    begin, end = engine.fasta_index(text, threads=max(1, (os.cpu_count() or 1) // world))
+    begin, end = _genome_index(genome, threads=max(1, (os.cpu_count() or 1) // world))
     n = int(begin.shape[0])
     _, _, dim = engine._lib.pattern_info(str(pattern))
     if n == 0:
@@ -213,8 +236,10 @@ def _profile_file_sharded(genome, pattern, strand, want, rank, world):
     shard = torch.zeros((n_max, dim), dtype=dtype, device=device)
     if hi > lo:
         byte_lo, byte_hi = int(begin[lo]), int(end[hi - 1])
-        res = engine.profile_text(np.ascontiguousarray(text[byte_lo:byte_hi]), str(pattern), strand, want,
-                                  begin[lo:hi] - byte_lo, end[lo:hi] - byte_lo)
+        d_text = engine.file_to_device(genome, byte_lo, byte_hi, device)
+        d_begin = torch.from_numpy(begin[lo:hi] - byte_lo).to(device)
+        d_end = torch.from_numpy(end[lo:hi] - byte_lo).to(device)
+        res = engine.profile_device(d_text, d_begin, d_end, str(pattern), strand, want)
         shard[:hi - lo].copy_(res[key])
     gathered = torch.empty((world * n_max, dim), dtype=dtype, device=device)
     dist.all_gather_into_tensor(gathered, shard)
@@ -302,7 +327,15 @@ def compute_distances_device(frequencies, metric="Eucl"):
     device = engine.require_cuda()
     X = torch.from_numpy(np.ascontiguousarray(np.asarray(frequencies))).to(device)
     rank, world = ranks()
-    if world == 1 or X.shape[0] < 2 * TILE * world:
+    if world == 1:
+        n = int(X.shape[0])
+        res = np.empty((n, n), dtype=np.float64)
+        if metric == "KT" and X.shape[1] < 2:
+            res.fill(1.0)  # kendall() with no element pair: distance 0 -> KT = 1
+        else:
+            _fill_host_matrix(res, X, metric)  # panels when the float64 matrix does not fit in HBM
+        return res
+    if X.shape[0] < 2 * TILE * world:
         res = engine.distance_matrix_device(X, metric, torch.float64, symmetric=True).cpu().numpy()
         return res if rank == 0 else None
     import torch.distributed as dist
@@ -331,98 +364,122 @@ def compute_distances_device(frequencies, metric="Eucl"):
     return res
 
 
-def _stream_rows(sink_array, X, metric):
-    """Fill the caller's (N, N) float32 array-like (memmap / HDF5 data region) with the matrix.
-    One GPU: row panels, upper triangle + mirror when the matrix fits in HBM.  Under torchrun:
-    every rank fills the rows it owns -- its paired block rows (upper triangle only, mirrored
-    tiles stored into the owner's rows over NVLink) when they fit in HBM, else plain row panels."""
-    rank, world = ranks()
-    metric = _large_metric(metric)
-    n = int(X.shape[0])
-
-    # A finished panel is copied from the pinned buffer into the file mapping by a few threads
-    # (numpy releases the GIL in the copy; one thread moves ~10 GB/s, the panels arrive at ~55 GB/s).
-    from concurrent.futures import ThreadPoolExecutor
-    workers = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
-    pool = ThreadPoolExecutor(workers) if workers > 1 else None
-
-    def _put(a, b, host, r0):
-        sink_array[a:b] = host[a - r0:b - r0]
-
-    def sink(r0, r1, host):
-        if pool is None or r1 - r0 < 4 * workers:
-            sink_array[r0:r1] = host
-            return
-        step = -(-(r1 - r0) // workers)
-        jobs = [pool.submit(_put, a, min(r1, a + step), host, r0) for a in range(r0, r1, step)]
-        for j in jobs:
-            j.result()
-
-    try:
-        _stream_rows_impl(sink, X, metric, n, rank, world)
-    finally:
-        if pool is not None:
-            pool.shutdown()
+_PREPARED = {}  # abspath -> hostsink.FileMatrix created early by main() (its pages are already being instantiated)
 
 
-def _stream_rows_impl(sink, X, metric, n, rank, world):
+def _my_row_ranges(n, rank, world):
+    """Row ranges this rank fills, in the order it fills them."""
     if world == 1:
-        engine.PanelStreamer(X, metric, torch.float32, PANEL_ROWS).run(sink)
-        return
-    from . import multigpu, sharding
+        return [(0, n)]
+    from . import sharding
     ranges = sharding.paired_row_ranges(n, world)
-    rows_owned = sum(ranges[i][1] - ranges[i][0] for i in sharding.owned_ranges(ranges, rank, world))
-    free, _ = torch.cuda.mem_get_info()
-    fits = torch.tensor([1 if rows_owned * n * 4 < 0.6 * free and n >= 2 * TILE * world else 0], device=X.device)
-    import torch.distributed as dist
-    dist.all_reduce(fits, op=dist.ReduceOp.MIN)  # every rank must take the same path
-    if int(fits.item()):
-        P, aux, dim = engine.prepare(X, metric)
-        job = multigpu.BlockRows(n, torch.float32, rank, world)
-        job.compute(metric, P, aux, dim)
-        panel = PANEL_ROWS or engine.auto_panel_rows(n, 4)
-        pinned = [torch.empty((panel, n), dtype=torch.float32).pin_memory() for _ in range(2)]
-        events, pending = [None, None], []
-        k = 0
-        for i in job.my_ranges:
-            a, b = job.ranges[i]
-            for r0 in range(a, b, panel):
-                r1 = min(b, r0 + panel)
-                slot = k & 1
-                while pending and pending[0][0] == slot:
-                    _, p0, p1 = pending.pop(0)
-                    events[slot].synchronize()
-                    sink(p0, p1, pinned[slot][:p1 - p0].numpy())
-                pinned[slot][:r1 - r0].copy_(job.out_rows[i][r0 - a:r1 - a], non_blocking=True)
-                events[slot] = torch.cuda.Event()
-                events[slot].record()
-                pending.append((slot, r0, r1))
-                k += 1
-        for slot, p0, p1 in pending:
-            events[slot].synchronize()
-            sink(p0, p1, pinned[slot][:p1 - p0].numpy())
-        job.close()
-    else:
-        for i in sharding.owned_ranges(ranges, rank, world):
-            a, b = ranges[i]
-            if b > a:
-                engine.PanelStreamer(X, metric, torch.float32, PANEL_ROWS, symmetric=False, rows=(a, b)).run(sink)
+    return [ranges[i] for i in sharding.owned_ranges(ranges, rank, world) if ranges[i][1] > ranges[i][0]]
+
+
+def _open_file_matrix(path, n, offset=0, create=True):
+    """The output region as a hostsink.FileMatrix whose pages (of this rank's rows) are being instantiated.
+    Rank 0 creates the file, the others attach after the barrier."""
+    rank, world = ranks()
+    fm = _PREPARED.pop(os.path.abspath(path), None)
+    if fm is not None and (fm.rows, fm.cols, fm.offset) == (n, n, offset):
+        return fm
+    if fm is not None:
+        fm.close()
+    if rank == 0:
+        fm = hostsink.FileMatrix(path, n, n, np.float32, offset, create=create)
+    _barrier()
+    if rank != 0:
+        fm = hostsink.FileMatrix(path, n, n, np.float32, offset, create=False)
+    threads = hostsink.host_threads(world)
+    fm.warm(_my_row_ranges(n, rank, world), threads=max(1, min(4, threads // 2)))
+    return fm
+
+
+def _fill_host_matrix(dest, X, metric):
+    """Fill the caller's (N, N) host array `dest` -- the mapping of the raw memmap file or of the HDF5
+    data region (float32), or the in-RAM result of the --large None conventions (float64) -- with the
+    matrix.  One GPU: row panels, upper triangle + mirror when the matrix fits in HBM; every finished
+    panel leaves through hostsink.RowShipper (DMA into a pinned ring, host threads into `dest`)
+    while the next one computes.  Under torchrun every rank fills the rows it owns -- its paired
+    block rows (upper triangle only, mirrored tiles stored into the owner's rows over NVLink) when
+    they fit in HBM, else plain row panels."""
+    rank, world = ranks()
+    n = int(X.shape[0])
+    if n == 0:
+        return
+    out_dtype = torch.float32 if dest.dtype == np.float32 else torch.float64
+    esize = dest.itemsize
+    threads = hostsink.host_threads(world)
+    # ring slots of at most 96 MB (page-locking costs ~0.5 s per GB), no larger than the job needs
+    slot = int(min(96 << 20, max(1 << 20, n * esize, n * n * esize // 2)))
+    shipper = hostsink.RowShipper(dest, slot_bytes=slot, copy_threads=max(1, min(8, threads - min(4, threads // 2))))
+    panel = PANEL_ROWS or 4096
+    panel = max(TILE, (int(panel) // TILE) * TILE)
+    try:
+        if world == 1:
+            free, _ = torch.cuda.mem_get_info()
+            P, aux, dim = engine.prepare(X, metric)
+            if n * n * esize < RESIDENT_FRACTION * free:
+                full = torch.empty((n, n), dtype=out_dtype, device=X.device)
+                for r0 in range(0, n, panel):
+                    r1 = min(n, r0 + panel)
+                    engine.distance_block(metric, P, aux, dim, r0, r1, 0, n, full, 0, 0, FLAG_SKIP_LOWER | FLAG_MIRROR)
+                    shipper.ship(full[r0:r1], r0, 0)  # rows [r0, r1) are final: earlier panels mirrored into them
+            else:
+                _fill_panels(shipper, metric, P, aux, dim, n, [(0, n)], panel, X.device, out_dtype)
+        else:
+            from . import multigpu, sharding
+            import torch.distributed as dist
+            ranges = sharding.paired_row_ranges(n, world)
+            rows_owned = sum(b - a for a, b in _my_row_ranges(n, rank, world))
+            free, _ = torch.cuda.mem_get_info()
+            fits = torch.tensor([1 if rows_owned * n * esize < RESIDENT_FRACTION * free and n >= 2 * TILE * world else 0], device=X.device)
+            dist.all_reduce(fits, op=dist.ReduceOp.MIN)  # every rank must take the same path
+            P, aux, dim = engine.prepare(X, metric)
+            if int(fits.item()):
+                job = multigpu.BlockRows(n, out_dtype, rank, world)
+                job.compute(metric, P, aux, dim, ship=shipper.ship)
+                shipper.finish()
+                shipper = None
+                job.close()
+            else:
+                _fill_panels(shipper, metric, P, aux, dim, n, _my_row_ranges(n, rank, world), panel, X.device, out_dtype)
+    finally:
+        if shipper is not None:
+            shipper.finish()
+
+
+def _fill_panels(shipper, metric, P, aux, dim, n, row_ranges, panel, device, out_dtype=torch.float32):
+    """Plain block rows (every entry computed) through two device panel buffers."""
+    bufs = [torch.empty((panel, n), dtype=out_dtype, device=device) for _ in range(2)]
+    busy = [None, None]
+    k = 0
+    for a, b in row_ranges:
+        for r0 in range(a, b, panel):
+            r1 = min(b, r0 + panel)
+            slot = k & 1
+            if busy[slot] is not None:
+                torch.cuda.current_stream().wait_event(busy[slot])  # its rows have left the device
+            engine.distance_block(metric, P, aux, dim, r0, r1, 0, n, bufs[slot], r0, 0, 0)
+            busy[slot] = shipper.ship(bufs[slot][:r1 - r0], r0, 0)
+            k += 1
+
+
+def _profiles_to_device(frequencies):
+    device = engine.require_cuda()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(frequencies))).to(device)
 
 
 def compute_distances_memmap(frequencies, freq_name, output, metric="Eucl"):
     """Raw row-major float32 N x N file at `output` (reference :394-427)."""
     _check_metric(metric)
-    device = engine.require_cuda()
     rank, _ = ranks()
-    n = frequencies.shape[0]
-    if rank == 0:
-        np.memmap(output, dtype=np.float32, shape=(n, n), mode="w+").flush()
-    _barrier()
-    distances = np.memmap(output, dtype=np.float32, shape=(n, n), mode="r+")
-    X = torch.from_numpy(np.ascontiguousarray(np.asarray(frequencies))).to(device)
-    _stream_rows(distances, X, metric)
-    distances.flush()
-    del distances
+    n = int(frequencies.shape[0])
+    fm = _open_file_matrix(output, n)
+    try:
+        _fill_host_matrix(fm.array, _profiles_to_device(frequencies), _large_metric(metric))
+    finally:
+        fm.close()
     _barrier()
     if rank == 0:
         remove_folder(os.path.dirname(freq_name))
@@ -431,16 +488,22 @@ def compute_distances_memmap(frequencies, freq_name, output, metric="Eucl"):
 def compute_distances_h5py(freq_name, dist_name, metric="Eucl"):
     """HDF5 file at `dist_name`, dataset 'distances' (N, N) float32 (reference :480-534)."""
     _check_metric(metric)
-    device = engine.require_cuda()
     rank, _ = ranks()
     freqs = io_formats.read_hdf5(freq_name, "frequencies")
-    n = freqs.shape[0]
-    X = torch.from_numpy(np.ascontiguousarray(freqs)).to(device)
-    if rank == 0:
-        io_formats.Hdf5DatasetWriter(dist_name, "distances", (n, n), np.float32).close()
-    _barrier()
-    with io_formats.Hdf5DatasetWriter.attach(dist_name, "distances") as writer:
-        _stream_rows(writer.mm, X, metric)
+    n = int(freqs.shape[0])
+    fm = _PREPARED.get(os.path.abspath(dist_name))
+    if fm is None:
+        if rank == 0:
+            io_formats.Hdf5DatasetWriter(dist_name, "distances", (n, n), np.float32).close()
+        _barrier()
+        _, _, offset = io_formats.dataset_location(dist_name, "distances")
+    else:
+        offset = fm.offset
+    fm = _open_file_matrix(dist_name, n, offset, create=False)
+    try:
+        _fill_host_matrix(fm.array, _profiles_to_device(freqs), _large_metric(metric))
+    finally:
+        fm.close()
     _barrier()
     if rank == 0:
         remove_folder(os.path.dirname(freq_name))
@@ -462,6 +525,38 @@ def compute_distances(mthdrun, large, frequencies, freq_name, out_file, dist, th
         print("Error, method {} is not implemented for pairwise distances computation".format(mthdrun),
               file=sys.stderr)
     return res
+
+
+def _warm_cuda():
+    try:
+        torch.cuda.init()
+        torch.empty(1, device="cuda")
+        engine._lib.load()
+    except Exception:  # the stages report the missing device / library themselves
+        pass
+
+
+def _prepare_outputs(params):
+    """Index the assembly and, when the distance stage will fill a file, create it now."""
+    if not os.path.isfile(params.genome) or params.strand not in ("both", "minus", "plus"):
+        return
+    begin, _ = _genome_index(params.genome)
+    n = int(begin.shape[0])
+    if n == 0 or params.mthdrun != "joblib" or params.dist not in METRICS:
+        return
+    out = os.path.abspath(params.out_file)
+    threads = hostsink.host_threads(1)
+    if params.large == "memmap":
+        fm = hostsink.FileMatrix(params.out_file, n, n, np.float32, 0, create=True)
+    elif params.large == "h5py":
+        writer = io_formats.Hdf5DatasetWriter(params.out_file, "distances", (n, n), np.float32)
+        offset = writer.data_off
+        writer.close()
+        fm = hostsink.FileMatrix(params.out_file, n, n, np.float32, offset, create=False)
+    else:
+        return
+    fm.warm([(0, n)], threads=max(1, min(4, threads // 2)))
+    _PREPARED[out] = fm
 
 
 # ---------------------------------------------------------------------------
@@ -513,9 +608,20 @@ def main(argv=None):
         os.makedirs(params.workdir)
     _barrier()
 
+    import threading
     import time
     verbose = os.environ.get("PO_VERBOSE") == "1" and rank == 0  # stage timings on stderr
     t0 = time.perf_counter()
+    if world == 1:
+        # While the CUDA context comes up (seconds on a fresh process) the host indexes the FASTA file
+        # and, for the --large outputs, creates the N x N file and starts instantiating its pages --
+        # the slowest part of the whole run on a fresh file (hostsink.py).
+        warm = threading.Thread(target=_warm_cuda, daemon=True)
+        warm.start()
+        try:
+            _prepare_outputs(params)
+        finally:
+            warm.join()
     say("Computing frequencies")
     frequencies, freq_name = compute_frequencies(params.mthdrun, params.large, params.genome, params.pattern,
                                                  params.strand, params.distchunksize, params.threads_max,

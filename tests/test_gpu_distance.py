@@ -109,7 +109,7 @@ def test_jsd_near_identical_profiles_keep_relative_accuracy():
     got = _gpu_matrix(X, "JSD")
     want = po.pairwise_np(X.astype(np.float64), "JSD")
     off = ~np.eye(len(rows), dtype=bool)
-    assert (np.abs(got[off] / want[off] - 1) < 2e-6).all()
+    assert (np.abs(got[off] / want[off] - 1) < RTOL).all()
 
 
 @pytest.mark.parametrize("metric", ["KT", "SC"])
@@ -131,6 +131,47 @@ def test_rank_metrics_exact(metric):
         assert np.array_equal(got, want)  # integer counts, same float64 expression: bit exact
 
 
+def test_spearman_k7_does_not_overflow():
+    """SC above 4096 dimensions runs on the CUDA cores; at dim = 16384 (k = 7) the rank products of
+    correlated rows exceed 2^31 within one 32-element chunk (and a single product does above
+    dim = 46341): the accumulation is 64-bit."""
+    dim = 4 ** 7
+    rng = np.random.default_rng(77)
+    X = rng.random((9, dim))
+    X[0] = np.arange(dim)            # extreme centred ranks +/-(dim-1), perfectly correlated with row 1
+    X[1] = np.arange(dim) * 2.0 + 5
+    X[2] = -np.arange(dim)           # and perfectly anti-correlated
+    X[3] = np.round(X[3] * 6)        # tie-heavy
+    X[4] = 1.0                       # constant row -> NaN
+    got = _gpu_matrix(X, "SC")
+    want = np.array([[po.SC(a, b) for b in X] for a in X])
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    m = ~np.isnan(want)
+    assert np.abs(got[m] - want[m]).max() < 1e-12
+    assert got[0, 1] == 0.0 and got[0, 2] == 2.0
+
+
+def test_jsd_sparse_k5_short_contigs_accuracy():
+    """C5-like profiles (k = 5, 5 kb contigs: about ten windows per bin, many exact zeros, so nearly
+    every term takes the log-based branch): 2 000 rows x 1024 dimensions against the float64 C oracle."""
+    from oracle import coracle
+    n = 2000
+    seqs = synth.make_sequences(n, 5000, seed=55)
+    text, begin, end = engine.sequences_to_text(seqs)
+    X = coracle.profile_batch(text, begin, end, "11111", "both").astype(np.float32)
+    X[17] = 0.0
+    assert (X == 0).mean() > 0.001
+    got = _gpu_matrix(X, "JSD", torch.float64)
+    want = coracle.pairwise_rows("JSD", X.astype(np.float64))
+    off = ~np.eye(n, dtype=bool)
+    rel = np.abs(got - want)[off] / want[off]
+    print("sparse k=5 JSD: max rel err %.3e, mean %.3e" % (rel.max(), rel.mean()))
+    assert rel.max() < RTOL
+    assert (np.diag(got) == 0).all() and np.array_equal(got, got.T)
+    got32 = _gpu_matrix(X, "JSD", torch.float32).astype(np.float64)
+    assert (np.abs(got32 - want)[off] / want[off]).max() < RTOL
+
+
 def test_rank_metrics_small_dims():
     rng = np.random.default_rng(2)
     for dim in (2, 3, 5, 16, 33, 64):
@@ -145,9 +186,9 @@ def test_rank_metrics_small_dims():
 
 def test_pair_api_and_block_rows():
     X = _profiles(130, 2500, "1111", seed=12)
-    assert phylodist.Eucl(X[0], X[1]) == pytest.approx(po.Eucl(X[0], X[1]), rel=2e-6)
-    assert phylodist.JSD(X[0], X[1]) == pytest.approx(po.JSD(X[0], X[1]), rel=2e-6)
-    assert phylodist.BC(X[0], X[1]) == pytest.approx(po.BC(X[0], X[1]), rel=2e-6)
+    assert phylodist.Eucl(X[0], X[1]) == pytest.approx(po.Eucl(X[0], X[1]), rel=RTOL)
+    assert phylodist.JSD(X[0], X[1]) == pytest.approx(po.JSD(X[0], X[1]), rel=RTOL)
+    assert phylodist.BC(X[0], X[1]) == pytest.approx(po.BC(X[0], X[1]), rel=RTOL)
     assert phylodist.KT(X[0], X[1]) == pytest.approx(po.KT(X[0], X[1]), abs=1e-12)
     assert phylodist.SC(X[0], X[1]) == pytest.approx(po.SC(X[0], X[1]), abs=1e-12)
     assert phylodist.KL(X[0], X[1]) == pytest.approx(po.KL(X[0], X[1]), rel=1e-12)
@@ -160,7 +201,7 @@ def test_pair_api_and_block_rows():
     got = phylodist.JSD(X32, X32[10:31])
     want = po.JSD(X32.astype(np.float64), X32[10:31].astype(np.float64))
     assert got.shape == (21, 130) and got.dtype == np.float32
-    assert np.allclose(got, want, rtol=2e-6, atol=1e-9)
+    assert np.allclose(got, want, rtol=RTOL, atol=1e-9)
     # block rows written at an offset, ragged edges (130 is not a multiple of 64)
     Xd = torch.from_numpy(X32).cuda()
     P, aux, dim = engine.prepare(Xd, "Eucl")
@@ -302,7 +343,7 @@ def test_full_size_matrix_properties(metric, n, dim):
         assert lo == 0.0 and hi <= np.log(2) * (1 + 1e-6)
         others = torch.ones(n, dtype=torch.bool, device="cuda")
         others[zero_row] = False
-        assert torch.allclose(M[zero_row][others], torch.full((n - 1,), np.log(2) / 2, device="cuda"), rtol=2e-6)
+        assert torch.allclose(M[zero_row][others], torch.full((n - 1,), np.log(2) / 2, device="cuda"), rtol=RTOL)
     elif metric == "SC":
         assert lo > -1e-6 and hi < 2.0 + 1e-6
     else:
@@ -317,7 +358,7 @@ def test_full_size_matrix_properties(metric, n, dim):
     want = np.array([fn(Xh[index[i]], Xh[index[j]]) for i, j in zip(ii, jj)])
     ok = ~np.isnan(want)
     assert np.array_equal(np.isnan(got), np.isnan(want))
-    tol = {"JSD": 2e-6, "EuclGram": RTOL_TC, "SC": 2e-6}[metric]  # float32 output
+    tol = {"JSD": RTOL, "EuclGram": RTOL_TC, "SC": RTOL}[metric]  # float32 output
     assert np.allclose(got[ok], want[ok], rtol=tol, atol=1e-7), np.abs(got[ok] - want[ok]).max()
     # row panels recomputed as plain block rows (every entry computed, no mirror)
     P, aux, d = engine.prepare(X, metric)
