@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--mean-len", type=int, default=20_000)
     ap.add_argument("--panel-rows", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra.configs block (C3, C4, C5 kernels)")
     ap.add_argument("--no-cli", action="store_true", help="skip the e2e_cli leg (dispatcher functions into a real memmap file)")
     ap.add_argument("--ring-sink", action="store_true",
                     help="end to end: copy whole row panels into a 2-slot pinned ring instead of a host matrix")
@@ -62,6 +63,14 @@ def parse_args():
 
 def workload_name(n, mean_len):
     return "C2: JSD k=4 strand=both, %d contigs x %d kb synthetic multi-FASTA" % (n, mean_len // 1000)
+
+
+def workload_config(n, mean_len):
+    """The `config` object of the JSON line: the same in both arms (ours and --impl reference)."""
+    return {"workload": workload_name(n, mean_len), "pattern": PATTERN, "strand": STRAND, "contigs": n,
+            "mean_contig_length": mean_len, "unique_pairs": n * (n + 1) // 2,
+            "l2": "inputs (~%.2f GB of FASTA text) and outputs (%.1f GB matrix) exceed the 126 MB L2; no flush needed"
+                  % (n * mean_len * 81 / 80 / 1e9, n * n * 4 / 1e9)}
 
 
 # ---------------------------------------------------------------------------
@@ -124,12 +133,25 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # CPU baselines (the oracle port; the only place bench.py executes oracle/)
 # ---------------------------------------------------------------------------
-def cpu_python_port_rates(seqs_sample, n_profile, n_dist, n_jobs):
+def _block_row_jsd(F, s):
+    """One worker of the reference's block-row split: D(X[s], X) (distances_loc, bin/phyloligo.py:195-207)."""
+    from sklearn.metrics import pairwise_distances
+    from oracle import phylo_oracle as po
+    return pairwise_distances(F[s], F, metric=po.JSD, n_jobs=1)
+
+
+def cpu_python_port_rates(seqs_sample, n_profile, n_dist, n_jobs, modes=("serial",)):
     """Time the Python restatement of the reference path the way the reference runs it
-    (joblib over sequences; sklearn.pairwise_distances with the callable metric,
-    bin/phyloligo.py:867-869, 388-390).  Returns (seconds per base, seconds per pair)."""
+    (joblib over sequences, bin/phyloligo.py:867-869; distances through sklearn.pairwise_distances
+    with the callable metric, :388-390, or its block rows fanned out to joblib workers, :423-424).
+    The distance stage is timed in every mode of `modes` and the FASTEST is kept, so that the
+    baseline is not handicapped by the GIL: "serial" (one core; sklearn evaluates the upper
+    triangle only), "threads" (pairwise_distances(n_jobs): threads in current sklearn) and
+    "processes" (block rows over loky worker processes, what the reference's joblib did).
+    Returns (seconds per base, seconds per unique pair, detail)."""
     from joblib import Parallel, delayed
     from sklearn.metrics import pairwise_distances
+    from sklearn.utils import gen_even_slices
     from oracle import phylo_oracle as po
 
     prof = [s.decode("latin-1") for s in seqs_sample[:n_profile]]
@@ -142,15 +164,25 @@ def cpu_python_port_rates(seqs_sample, n_profile, n_dist, n_jobs):
         extra = [po.frequency_np(s, PATTERN, STRAND) for s in seqs_sample[F.shape[0]:n_dist]]
         F = np.vstack([F] + extra) if extra else F
     F = F[:n_dist]
-    t0 = time.perf_counter()
-    D = pairwise_distances(F, metric=po.JSD, n_jobs=n_jobs)
-    t_dist = time.perf_counter() - t0
     n = F.shape[0]
-    evaluated = n * (n + 1) // 2 if n_jobs == 1 else n * n  # sklearn: triangle only when serial
-    assert D.shape == (n, n)
-    return t_prof / max(1, bases), t_dist / max(1, n * (n + 1) // 2), dict(
-        profile_contigs=len(prof), profile_bases=bases, profile_s=t_prof, dist_rows=n, dist_evaluations=evaluated,
-        dist_s=t_dist)
+    unique = n * (n + 1) // 2
+    times = {}
+    for mode in modes:
+        t0 = time.perf_counter()
+        if mode == "serial":
+            D = pairwise_distances(F, metric=po.JSD, n_jobs=1)
+        elif mode == "threads":
+            D = pairwise_distances(F, metric=po.JSD, n_jobs=n_jobs)
+        else:
+            blocks = Parallel(n_jobs=n_jobs)(delayed(_block_row_jsd)(F, s) for s in gen_even_slices(n, n_jobs))
+            D = np.vstack(blocks)
+        times[mode] = time.perf_counter() - t0
+        assert D.shape == (n, n)
+    best = min(times, key=times.get)
+    t_dist = times[best]
+    return t_prof / max(1, bases), t_dist / max(1, unique), dict(
+        profile_contigs=len(prof), profile_bases=bases, profile_s=t_prof, dist_rows=n, dist_s=t_dist,
+        dist_mode=best, dist_seconds_by_mode=times)
 
 
 def cpu_c_port_rates(seqs_sample, n_profile, n_dist, threads):
@@ -205,25 +237,27 @@ def run_reference(args):
     total_bases = n_contigs * args.mean_len
     cores = os.cpu_count() or 1
     n_profile = min(n_contigs, max(64, 8 * cores))  # a few seconds of work per step on all cores
-    n_dist = min(n_contigs, 400)
+    n_dist = min(n_contigs, 600)
     seqs = sample_sequences(max(n_profile, n_dist), args.mean_len)
     vals, detail = [], None
     for it in range(args.warmup + args.steps):
-        spb, spp, detail = cpu_python_port_rates(seqs, n_profile, n_dist, cores)
+        spb, spp, detail = cpu_python_port_rates(seqs, n_profile, n_dist, cores, modes=("serial", "threads", "processes"))
         if it >= args.warmup:
             vals.append((spb, spp))
     spb = float(np.mean([v[0] for v in vals]))
     spp = float(np.mean([v[1] for v in vals]))
     value = whole_job_pairs_per_s(n_contigs, total_bases, spb, spp)
     step_ms = 1e3 * (detail["profile_s"] + detail["dist_s"])
-    sample = ("Python port of the reference joblib path, %d threads: %d contigs profiled, %d profiles all-pairs JSD "
-              "via sklearn.pairwise_distances(callable); value = whole-job pairs/s implied for the workload"
-              % (cores, n_profile, n_dist))
+    sample = ("Python port of the reference joblib path on %d cores: %d contigs profiled by joblib worker processes, %d profiles "
+              "all-pairs JSD timed three ways (serial / sklearn threads / block rows over joblib worker processes), fastest kept: "
+              "%s (%s); value = whole-job pairs/s those rates imply for the workload"
+              % (cores, n_profile, n_dist, detail["dist_mode"],
+                 ", ".join("%s %.2f s" % kv for kv in sorted(detail["dist_seconds_by_mode"].items()))))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(n_contigs, args.mean_len), "pattern": PATTERN, "strand": STRAND},
+        "config": workload_config(n_contigs, args.mean_len),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "seconds_per_base": spb, "seconds_per_pair": spp},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -235,6 +269,152 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
+def run_extra_configs(device, scale, hbm_peak, bf16_peak, fp32_peak):
+    """BASELINE.json configs[2..4] on one GPU, device-resident kernels timed with CUDA events in this
+    same process (same clocks record as the headline): C3 spaced pattern 111010011 (4096 dims) Eucl
+    (Gram form, tensor cores) and BC on 50 000 reads x 15 kb; C4 Kendall / Spearman on 20 000
+    tie-heavy short sequences; C5 JSD k=5 at N = 1 000 000 contigs x 5 kb on a stated sample of row
+    panels (the 4 TB matrix is streamed panel by panel, never resident), extrapolated explicitly."""
+    import torch
+    from phyloligo_b200 import _lib, engine, synth
+    from phyloligo_b200._lib import FLAG_MIRROR, FLAG_SKIP_LOWER
+
+    def timed(fn, reps):
+        fn()  # warm-up (first launch of a kernel configures its shared-memory opt-in)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def matrix_stage(X, metric, reps, flop_per_pair, peak, peak_unit, bound):
+        n = int(X.shape[0])
+        P, aux, dim = engine.prepare(X, metric)
+        out = torch.empty((n, n), dtype=torch.float32, device=device)
+        ms_prep = timed(lambda: engine.prepare(X, metric), 1)
+        ms = timed(lambda: engine.distance_block(metric, P, aux, dim, 0, n, 0, n, out, 0, 0, FLAG_SKIP_LOWER | FLAG_MIRROR), reps)
+        pairs = n * (n + 1) // 2
+        tile = {"JSD": (32, 64), "EuclGram": (128, 128)}.get(metric, (64, 64))
+        if metric == "SC" and 64 <= dim <= 4096:
+            tile = (128, 128)
+        computed = sum((min(n, t0 + tile[0]) - t0) * (n - (t0 // tile[1]) * tile[1]) for t0 in range(0, n, tile[0]))
+        achieved = computed * flop_per_pair / (ms * 1e-3) / 1e12
+        res = {"metric": metric, "kernel_ms": ms, "prepare_ms": ms_prep, "unique_pairs_per_s": pairs / (ms * 1e-3),
+               "pairs_computed": computed,
+               "roofline": {"bound": bound, "achieved": achieved, "peak": peak, "unit": peak_unit,
+                            "frac": achieved / peak if peak else None, "work_per_pair": flop_per_pair}}
+        del out, P, aux
+        torch.cuda.empty_cache()
+        return res
+
+    extras = {}
+    popc_peak = _lib.microbench(2)
+    # ---- C3 ----
+    n3 = max(256, int(round(50_000 * scale)))
+    text, b, e, bases = synth.device_fasta(n3, 15_000, 3, device)
+    prof = lambda: engine.profile_device(text, b, e, "111010011", "both", want=("freq32",))  # noqa: E731
+    ms_prof = timed(prof, 2)
+    X = prof()["freq32"]
+    c3 = {"workload": "C3: pattern 111010011 (4096 dims) strand both, %d reads x 15 kb (fixed-length synthetic, generated on the device)" % n3,
+          "profiling": {"kernel_ms": ms_prof, "gbases_per_s": bases / (ms_prof * 1e-3) / 1e9,
+                        "roofline": {"bound": "hbm", "achieved": (int(text.shape[0]) + n3 * 4096 * 4) / (ms_prof * 1e-3) / 1e9,
+                                     "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": (int(text.shape[0]) + n3 * 4096 * 4) / (ms_prof * 1e-3) / 1e9 / hbm_peak}},
+          "stages": []}
+    del text
+    c3["stages"].append(matrix_stage(X, "EuclGram", 3, 2 * 4096, bf16_peak, "TFLOP/s", "tensor"))
+    c3["stages"].append(matrix_stage(X, "BC", 1, 5 * 4096, fp32_peak, "TFLOP/s", "fp32"))
+    extras["C3"] = c3
+    del X
+    torch.cuda.empty_cache()
+    # ---- C4 ----
+    n4 = max(256, int(round(20_000 * scale)))
+    seqs = synth.make_sequences(n4, 375, 4, "short", all_n_frac=0.005)
+    res = engine.profile_text(np.frombuffer(synth.to_fasta_bytes(seqs), dtype=np.uint8), "1111", "both", want=("freq32",))
+    X = res["freq32"]
+    c4 = {"workload": "C4: k=4 on %d tie-heavy short sequences (150-600 bp, 0.5 %% empty / all-N)" % n4, "stages": []}
+    kt = matrix_stage(X, "KT", 2, 256 * 255 // 2, popc_peak * 16.0, "1e12 element-pair classifications/s", "popc")
+    kt["roofline"]["note"] = ("work = D(D-1)/2 element-pair classifications per pair (SURVEY.md 8d); peak = measured POPC rate x 16 "
+                              "(a 32-bit word classifies 32 element pairs with 2 POPC)")
+    c4["stages"].append(kt)
+    c4["stages"].append(matrix_stage(X, "SC", 3, 2 * 256, bf16_peak, "TFLOP/s", "tensor"))
+    extras["C4"] = c4
+    del X
+    torch.cuda.empty_cache()
+    # ---- C5 at N = 1M: a sample of row panels ----
+    n5 = max(2048, int(round(1_000_000 * scale)))
+    text, b, e, bases = synth.device_fasta(n5, 5_000, 5, device)
+    prof = lambda: engine.profile_device(text, b, e, "11111", "both", want=("freq32",))  # noqa: E731
+    ms_prof = timed(prof, 1)
+    X = prof()["freq32"]
+    text_bytes = int(text.shape[0])
+    del text
+    torch.cuda.empty_cache()
+    P, aux, dim = engine.prepare(X, "JSD")
+    rows = 1024
+    bufs = [torch.empty((rows, n5), dtype=torch.float32, device=device) for _ in range(2)]
+    ring = [torch.empty((rows, n5), dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    starts = [0, (n5 // 2) // rows * rows, max(0, (n5 - 4 * rows) // rows * rows)]
+    kernel_ms, stream_ms = [], []
+    for r_first in starts:
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        engine.distance_block("JSD", P, aux, dim, r_first, min(n5, r_first + rows), 0, n5, bufs[0], r_first, 0, 0)  # warm-up
+        torch.cuda.synchronize()
+        k0.record()
+        engine.distance_block("JSD", P, aux, dim, r_first, min(n5, r_first + rows), 0, n5, bufs[0], r_first, 0, 0)
+        k1.record()
+        torch.cuda.synchronize()
+        kernel_ms.append(k0.elapsed_time(k1))
+        # four consecutive panels, each copied to pinned host memory while the next one computes
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        free = [None, None]
+        s0.record()
+        for k in range(4):
+            r0 = r_first + k * rows
+            if r0 >= n5:
+                break
+            slot = k & 1
+            if free[slot] is not None:
+                torch.cuda.current_stream().wait_event(free[slot])
+            engine.distance_block("JSD", P, aux, dim, r0, min(n5, r0 + rows), 0, n5, bufs[slot], r0, 0, 0)
+            ready = torch.cuda.Event()
+            ready.record()
+            copy_stream.wait_event(ready)
+            with torch.cuda.stream(copy_stream):
+                ring[slot].copy_(bufs[slot], non_blocking=True)
+                free[slot] = torch.cuda.Event()
+                free[slot].record(copy_stream)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        s1.record()
+        torch.cuda.synchronize()
+        stream_ms.append(s0.elapsed_time(s1) / 4)
+    km, sm_ = float(np.mean(kernel_ms)), float(np.mean(stream_ms))
+    panels = -(-n5 // rows)
+    achieved = rows * n5 * 10 * dim / (km * 1e-3) / 1e12
+    extras["C5"] = {
+        "workload": "C5: JSD k=5 (1024 dims) strand both, %d contigs x 5 kb (fixed-length synthetic, generated on the device), "
+                    "--large memmap style row panels" % n5,
+        "profiling": {"kernel_ms": ms_prof, "gbases_per_s": bases / (ms_prof * 1e-3) / 1e9,
+                      "roofline": {"bound": "hbm", "achieved": (text_bytes + n5 * 1024 * 4) / (ms_prof * 1e-3) / 1e9, "peak": hbm_peak,
+                                   "unit": "GB/s", "frac": (text_bytes + n5 * 1024 * 4) / (ms_prof * 1e-3) / 1e9 / hbm_peak}},
+        "sample": "row panels of %d rows x %d columns at rows %s (every entry of the panel computed: the %.1f TB matrix is never "
+                  "resident, so the symmetry shortcut does not apply); kernel alone, and 4 consecutive panels with the D2H of each "
+                  "(%.1f GB into pinned memory) overlapped with the next" % (rows, n5, starts, n5 * n5 * 4 / 1e12, rows * n5 * 4 / 1e9),
+        "kernel_ms_per_panel": kernel_ms, "streamed_ms_per_panel": stream_ms,
+        "entries_per_s_kernel": rows * n5 / (km * 1e-3), "entries_per_s_streamed": rows * n5 / (sm_ * 1e-3),
+        "extrapolation": {"panels": panels, "one_gpu_s": panels * sm_ * 1e-3, "eight_gpus_s": panels * sm_ * 1e-3 / 8,
+                          "how": "panels x streamed ms per panel; row panels are independent, so 8 GPUs take 1/8 "
+                                 "(host side: 4 TB through 8 x PCIe into the memmap)"},
+        "roofline": {"bound": "fp32", "kernel": "jsd_tile_kernel<float>", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp32_peak if fp32_peak else None, "flop_convention": "10 flop per dimension per entry, D=1024"},
+    }
+    return extras
+
+
 def run_cli_leg(fasta, n_contigs, pairs_unique, rank, world, device, want_rows):
     """The call a user of the reference makes: phyloligo.compute_frequencies(...) then
     phyloligo.compute_distances("joblib", "memmap", ...) (reference bin/phyloligo.py:980-997, 536-553)
@@ -569,6 +749,7 @@ def run_ours(args):
     # ---- the drop-in path itself: compute_frequencies + compute_distances(... "memmap" ...) into a real file ----
     e2e_cli = None
     peer_exchange = job is not None and job.peers is not None
+    had_host_result = host_result is not None
     if not args.no_cli:
         sample_rows = [0, n_contigs // 3, n_contigs - 1]
         want_rows = {r: matrix_row(r) for r in sample_rows}  # collective under torchrun (all-gather of profiles)
@@ -606,18 +787,16 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": workload_name(n_contigs, args.mean_len), "pattern": PATTERN, "strand": STRAND,
-                "total_bases": total_bases, "unique_pairs": pairs_unique,
+            "config": workload_config(n_contigs, args.mean_len),
+            "detail": {
+                "total_bases": total_bases,
                 "pairs_computed_per_step_rank0": pairs_per_step_computed,
                 "parallelism": "1 GPU, upper triangle + mirror" if world == 1 else
                                "%d ranks: records sharded, NCCL all-gather of profiles, paired block rows (s, 2W-1-s), "
                                "transposed off-diagonal tiles %s" % (world, "stored by the tile kernel into the owner's rows over NVLink "
                                "(CUDA IPC peer memory)" if peer_exchange else "exchanged over NCCL send/recv"),
-                "l2": "inputs (%.2f GB text) and outputs (%.1f GB matrix) exceed the 126 MB L2; no flush needed"
-                      % (len(fasta) / 1e9, n_contigs * n_contigs * 4 / 1e9),
                 "e2e_sink": ("the result matrix in pinned host memory (%.1f GB per rank); finished blocks leave by strided "
-                             "DMA (po_copy2d_async) while the next panel computes" % (host_bytes / 1e9)) if host_result is not None
+                             "DMA (po_copy2d_async) while the next panel computes" % (host_bytes / 1e9)) if had_host_result
                             else "row panels of %d rows copied D2H into a 2-slot pinned ring (discard sink)" % panel,
             },
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
@@ -647,6 +826,11 @@ def run_ours(args):
                 "distance_ms_per_step": dist_ms / max(1, args.steps),
             },
         }
+        if world == 1 and not args.no_extra:
+            bf16_peak = float(peaks.get("bf16_tflops", 1665.5))
+            line["extra"] = {"configs": run_extra_configs(device, args.scale, hbm_peak, bf16_peak, fp32_peak),
+                             "peaks": {"hbm_gbs": hbm_peak, "bf16_tflops_burst": bf16_peak, "fp32_ffma_tflops": fp32_peak,
+                                       "source": "MEASURED_PEAKS.json (HBM, bf16 burst); po_microbench in this run (FP32, POPC)"}}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             # about 10-15 s of single-core CPU work: 300 contigs profiled (~1 us per base), 700 profiles all-pairs

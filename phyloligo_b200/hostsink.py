@@ -116,6 +116,7 @@ class FileMatrix:
         for r0, r1 in row_ranges:
             lo, hi = self.row_bytes(r0, r1)
             ranges.append((lo // page * page, min(self.offset + self.nbytes, -(-hi // page) * page)))
+        threads = int(os.environ.get("PO_SINK_WARM_THREADS", "0")) or threads
         self.warmer = PageWarmer(self.fd, self.base, ranges, threads)
         self.warmer.start()
 
@@ -163,26 +164,40 @@ class RowShipper:
     ``dest[row0 + ..., col0 : col0 + width]`` with `copy_threads` threads.  ``finish()`` drains.
     """
 
-    def __init__(self, dest, slot_bytes=96 << 20, slots=3, copy_threads=4):
+    def __init__(self, dest, slot_bytes=32 << 20, slots=4, copy_threads=4):
         if dest.ndim != 2 or dest.strides[1] != dest.itemsize:
             raise PhyloligoError("RowShipper: destination rows must be contiguous")
         self.dest = dest
         self.dst_pitch = int(dest.strides[0])
         self.esize = int(dest.itemsize)
         self.tdtype = {4: torch.float32, 8: torch.float64}[self.esize]
-        self.slot_elems = int(slot_bytes) // self.esize
-        self.pinned = [torch.empty(self.slot_elems, dtype=self.tdtype).pin_memory() for _ in range(slots)]
+        slot_bytes = int(os.environ.get("PO_SINK_SLOT_MB", "0")) << 20 or int(slot_bytes)
+        self.slot_elems = max(int(slot_bytes) // self.esize, int(dest.shape[1]))
+        self.pinned = [None] * slots
         self.free = queue.Queue()
-        for s in range(slots):
-            self.free.put(s)
         self.work = queue.Queue()
         self.copy_stream = torch.cuda.Stream()
-        self.copy_threads = max(1, int(copy_threads))
+        self.copy_threads = int(os.environ.get("PO_SINK_COPY_THREADS", "0")) or max(1, int(copy_threads))
         self.bytes_shipped = 0
         self.error = None
         self.lib = _lib.load()
+        self.device = torch.cuda.current_device()
+        # page-locking host memory is slow (~2 GB/s here): the slots are allocated by a helper thread and
+        # join the ring one by one, so the first panel's DMA starts after one slot, not after all of them
+        self.alloc_thread = threading.Thread(target=self._allocate, daemon=True)
+        self.alloc_thread.start()
         self.thread = threading.Thread(target=self._copier, daemon=True)
         self.thread.start()
+
+    def _allocate(self):
+        try:
+            torch.cuda.set_device(self.device)
+            for s in range(len(self.pinned)):
+                self.pinned[s] = torch.empty(self.slot_elems, dtype=self.tdtype).pin_memory()
+                self.free.put(s)
+        except Exception as exc:
+            self.error = exc
+            self.free.put(-1)
 
     def _copier(self):
         while True:
@@ -223,6 +238,8 @@ class RowShipper:
             if self.error is not None:
                 self.free.put(slot)
                 raise self.error
+            if slot < 0:
+                raise PhyloligoError("RowShipper: no pinned slot could be allocated")
             host = self.pinned[slot][: m * width].view(m, width)
             engine.copy2d(host, src[a:a + m], self.copy_stream)
             ev = torch.cuda.Event()
@@ -235,5 +252,6 @@ class RowShipper:
     def finish(self):
         self.work.put(None)
         self.thread.join()
+        self.alloc_thread.join()
         if self.error is not None:
             raise self.error

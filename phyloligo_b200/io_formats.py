@@ -8,8 +8,15 @@
   (reference :471-478, :923-930, :787-792).  The writer below emits the classic
   HDF5 layout (superblock v0, symbol-table root group, v1 object headers,
   contiguous storage) so h5py / libhdf5 consumers can open it; the reader parses
-  that same subset.  It has been checked against its own reader only -- libhdf5
-  is not available in the build image.
+  that same subset.  Neither h5py nor libhdf5 exists in the build image or on the GPU
+  boxes (probed, profiles/r02_env_probe.log), so the files cannot meet the library
+  itself; instead tests/test_hdf5_spec.py checks them with an independent byte-level
+  walker of the published format that is pinned to a file libhdf5 did write (a MATLAB
+  7.3 fixture of scipy's test data).
+  Reader limits: superblock version 0, old-style (symbol table) groups, version-1
+  object headers, contiguous layout, float32 / float64 -- i.e. files of this writer and
+  of libhdf5 with its default (earliest) format; chunked or compact datasets and the
+  superblock 2 / 3 files of ``libver="latest"`` are rejected with ValueError.
 """
 from __future__ import annotations
 

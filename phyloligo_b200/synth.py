@@ -167,3 +167,58 @@ def fast_fasta_bytes(n, mean_len, seed, model="lognormal", line=LINE):
             o2 = o + full * (line + 1)
             out[o2:o2 + rem] = s[full * line:]
     return out, total
+
+
+def device_fasta(n, length, seed, device, line=LINE, chunk_elems=1 << 26):
+    """Fixed-length variant ("fixed-length variant for roofline runs") generated on the
+    device: n records of `length` bases, the same GC mixture, N runs and soft-masked stretches,
+    80-column lines, headers ``>c{index}`` zero-padded to a fixed width.  For the configurations
+    whose FASTA text (5 GB at C5) would take minutes to draw on the host.
+    Returns (text uint8 tensor [n * record_bytes + 64], begin int64 [n], end int64 [n], total_bases)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(int(seed))
+    w = len(str(max(1, n - 1)))
+    hlen = 2 + w + 1
+    nl = -(-length // line)
+    rec = hlen + length + nl
+    text = torch.empty(n * rec + 64, dtype=torch.uint8, device=device)
+    text[n * rec:] = 10
+    recs = text[: n * rec].view(n, rec)
+    idx = torch.arange(n, device=device, dtype=torch.int64)
+    recs[:, 0] = ord(">")
+    recs[:, 1] = ord("c")
+    for d in range(w):
+        recs[:, 2 + d] = ((idx // (10 ** (w - 1 - d))) % 10 + 48).to(torch.uint8)
+    recs[:, 2 + w] = 10
+    body = recs[:, hlen:]
+    body[:, :] = 10  # newline columns; the base columns are overwritten below
+    contaminant = torch.rand(n, generator=g, device=device) < 0.10
+    gc = torch.where(contaminant, 0.66 + 0.03 * torch.randn(n, generator=g, device=device),
+                     0.52 + 0.03 * torch.randn(n, generator=g, device=device)).clamp_(0.05, 0.95)
+    col = torch.arange(length, device=device, dtype=torch.int64)
+    dst = col + col // line  # column of base j inside the record body (one newline after every `line` bases)
+    lut = torch.tensor([ord("A"), ord("T"), ord("C"), ord("G")], dtype=torch.uint8, device=device)
+    rows_per = max(1, chunk_elems // max(1, length))
+    for r0 in range(0, n, rows_per):
+        r1 = min(n, r0 + rows_per)
+        u = torch.randint(0, 1 << 16, (r1 - r0, length), generator=g, device=device, dtype=torch.int32)
+        is_gc = (u >> 1).to(torch.float32) < (gc[r0:r1, None] * 32768.0)
+        codes = (is_gc.to(torch.int64) << 1) | (u & 1).to(torch.int64)
+        body[r0:r1].index_copy_(1, dst, lut[codes])
+    # N runs (~0.1 % of positions, width 55) and soft-masked stretches (~5 %, width 275): at most one per record
+    for prob, width, kind in ((length * 0.001 / 55.0, 55, "n"), (length * 0.05 / 275.0, 275, "low")):
+        if length <= width:
+            continue
+        pick = torch.nonzero(torch.rand(n, generator=g, device=device) < min(1.0, prob)).flatten()
+        if pick.numel() == 0:
+            continue
+        start = torch.randint(0, length - width, (pick.numel(),), generator=g, device=device)
+        pos = dst[(start[:, None] + torch.arange(width, device=device)[None, :])]
+        flat = (pick[:, None] * rec + hlen + pos).flatten()
+        if kind == "n":
+            text[flat] = ord("N")
+        else:
+            text[flat] = text[flat] | 0x20
+    begin = idx * rec + hlen
+    end = begin + length + nl
+    return text, begin, end, n * length
