@@ -7,11 +7,13 @@ pinned buffers and a pool of host threads moves each finished slot into the mapp
 (po_host_copy2d) while the next slot is in flight and the next panel computes.
 
 What bounds this on a fresh output file is neither PCIe (52 GB/s) nor the host copy (90 GB/s into
-resident pages) but the kernel instantiating the file's pages: 8-14 GB/s on the boxes of this pool
-whatever the thread count (profiles/r02_sink_probe.log).  ``PageWarmer`` therefore starts
-instantiating pages (fallocate + populate, in row order) the moment the file exists -- while the
-CUDA context comes up, the FASTA is profiled and the first panels compute -- so that the copies
-land on resident pages.  Page-locking the mapping itself (po_host_register) so that the DMA lands
+resident, mapped pages) but the kernel instantiating and mapping the file's 4 KB pages: allocation
+(fallocate: 14 GB/s), zeroing + mapping (populate: 8-13 GB/s) whatever the thread count on the boxes
+of this pool, 5.7 GB/s for the whole chain and 12-14 GB/s when the file's pages already exist
+(profiles/r02_sink_probe.log, r02_cli_sink_bench.log; tmpfs huge pages are disabled there).
+``PageWarmer`` starts that work (fallocate + populate, in row order) the moment the file exists
+-- while the CUDA context comes up, the FASTA is profiled and the first panels compute -- so that
+as much of it as possible is off the critical path.  Page-locking the mapping itself (po_host_register) so that the DMA lands
 in the file directly costs more than it saves here (6 GB/s on top of the instantiation) and is
 refused by file systems with dirty tracking; the entry point stays in the C ABI
 (``FileMatrix.register``) for hosts where it pays.

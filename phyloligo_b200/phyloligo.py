@@ -410,8 +410,8 @@ def _fill_host_matrix(dest, X, metric):
     out_dtype = torch.float32 if dest.dtype == np.float32 else torch.float64
     esize = dest.itemsize
     threads = hostsink.host_threads(world)
-    # ring slots of at most 32 MB (page-locking costs ~0.5 s per GB), no larger than the job needs
-    slot = int(min(32 << 20, max(1 << 20, n * esize, n * n * esize // 2)))
+    # ring slots of at most 64 MB (page-locking costs ~0.5 s per GB: they join the ring one by one), no larger than the job needs
+    slot = int(min(64 << 20, max(1 << 20, n * esize, n * n * esize // 2)))
     shipper = hostsink.RowShipper(dest, slot_bytes=slot, copy_threads=max(1, min(8, threads - min(4, threads // 2))))
     panel = PANEL_ROWS or 4096
     panel = max(TILE, (int(panel) // TILE) * TILE)
