@@ -43,7 +43,6 @@ namespace po {
 constexpr int GT = 128;                 // tile edge (M = N = 128)
 constexpr int GK = 64;                  // K elements per block (4 MMAs of K = 16)
 constexpr int GBLOCK_BYTES = GT * GK * 2;     // one operand block: 16 KB
-constexpr int GTHREADS = 512;             // 16 warps: two of them also drive the pipeline, all 16 share the epilogue
 constexpr int GRASTER = 16;             // 128-column groups per rasterisation chunk
 constexpr float GSCALE = 16384.0f;      // 2^14
 constexpr double GUNSCALE = 1.0 / (16384.0 * 16384.0);
@@ -330,158 +329,179 @@ struct GramParams {
 };
 
 
-// Tile geometry per mode.  Eucl: the CTA computes 128 rows x 256 columns (two 128-column groups that
-// share the row operand in shared memory: a quarter less operand traffic out of L2, which is what
-// bounds the kernel at large K), with two accumulators per group -- hi.hi and hi.lo + lo.hi -- so
-// that both groups fit the 512 TMEM columns; the K stage is 32 wide (48 KB) in a 4-deep ring.
-// SC: 128 x 128, four exact integer accumulators (hh, hl, lh, ll), 64-wide stages (64 KB) in a 3-deep ring.
+// Tile geometry per mode.
+// Eucl: a CTA of 8 warps computes one 128 x 128 tile with two accumulators -- hi.hi and hi.lo + lo.hi --
+// in 256 TMEM columns, 32-wide K stages (32 KB) in a 3-deep ring: 97 KB of shared memory, so that TWO
+// CTAs are resident per SM.  While one CTA drains its accumulators (tcgen05.ld, float64 epilogue,
+// stores), the other one's MMAs keep the tensor pipe busy, and when both are in their main loops the
+// pipe interleaves their MMAs, which also hides the bubble between two dependent MMAs into one
+// accumulator (the cross terms).  (Round 1 ran one CTA of 16 warps per SM on 128 x 256 tiles: the
+// tensor pipe idled through every epilogue, ncu: pipe 56 % active, 14 of 16 warps parked at a barrier.)
+// SC: 128 x 128, four exact integer accumulators (hh, hl, lh, ll) = all 512 TMEM columns, 64-wide
+// stages (64 KB) in a 3-deep ring, one CTA of 16 warps per SM.
 template <int MODE> struct GramCfg;
-#ifndef GRAM_EUCL_NB
-#define GRAM_EUCL_NB 2
+#ifndef GRAM_EUCL_STAGES
+#define GRAM_EUCL_STAGES 3
+#endif
+#ifndef GRAM_EUCL_KS
+#define GRAM_EUCL_KS 32
 #endif
 template <> struct GramCfg<GM_EUCL> {
-    static constexpr int NB = GRAM_EUCL_NB, KS = (GRAM_EUCL_NB == 2 ? 32 : 64), STAGES = (GRAM_EUCL_NB == 2 ? 4 : 3), GROUP_COLS = 256;
+    static constexpr int NB = 1, KS = GRAM_EUCL_KS, STAGES = GRAM_EUCL_STAGES, GROUP_COLS = 256, TMEM_COLS = 256;
+    static constexpr int THREADS = 256, CTAS = 2;
 };
-template <> struct GramCfg<GM_SC>   { static constexpr int NB = 1, KS = 64, STAGES = 3, GROUP_COLS = 384; };
+template <> struct GramCfg<GM_SC> {
+    static constexpr int NB = 1, KS = 64, STAGES = 3, GROUP_COLS = 384, TMEM_COLS = 512;
+    static constexpr int THREADS = 512, CTAS = 1;
+};
 
-// Epilogue of one 128 x 128 group of a tile.  Warp w owns TMEM lanes 32 (w & 3) .. +31 (the rows a
-// warp may read) and the 32 columns 32 (w >> 2) .. +31, in two chunks of 16.  Mirrored entries are
+// Epilogue of one 128 x 128 group of a tile, by all warps of the CTA.  Warp w owns TMEM lanes
+// 32 (w & 3) .. +31 (the rows a warp may read) and the columns (128 / NCQ) (w >> 2) .. of the group,
+// NCQ = warps / 4, which it walks in blocks of 32 (two tcgen05.ld chunks of 16).  Mirrored entries are
 // stored straight from the registers (lanes = consecutive rows = consecutive addresses of the
-// mirrored row); the direct entries go through a shared-memory transpose so that a warp stores 128
-// contiguous bytes of one output row per instruction.  The operand ring is free by now.  Addresses
-// are one 64-bit base per thread plus small offsets; INTERIOR groups carry no per-entry bounds tests.
+// mirrored row); the direct entries go through a per-warp 32 x 33 shared-memory transpose so that a
+// warp stores 128 contiguous bytes of one output row per instruction.  The operand ring is free by
+// now.  INTERIOR groups carry no per-entry bounds tests.
 //
 // Eucl, diagonal group (row_base == col_base): with the cross terms hi.lo and lo.hi sharing one
 // accumulator, (r, c) and (c, r) of the same group see their products in a different order.  The
-// entries on and right of the diagonal are authoritative; the ones left of it are read back
-// transposed from a 128 x 129 shared-memory copy of the group (DIAG).  Groups wholly below the
-// diagonal get the same effect from the MMA issue order (see the kernel).
+// entries on and right of the diagonal are authoritative: the thread that holds (r, c), c > r, also
+// stores it at (c, r) of the same group -- the mirror store of an off-diagonal group, aimed at the
+// group itself -- and the computed values left of the diagonal are dropped, whatever the flags, so
+// that a block row computed on its own equals the rows of the symmetric run bit for bit.  Groups
+// wholly below the diagonal get the same effect from the MMA issue order (see the kernel).
 template <typename OUT_T, int MODE, bool INTERIOR, bool DIAG>
 __device__ __forceinline__ void gram_epilogue(const GramParams& p, unsigned tmem, int64_t row_base, int64_t col_base,
                                               const double* s_nb, unsigned char* gsmem) {
+    constexpr int NCQ = GramCfg<MODE>::THREADS / 128;  // column slices of the group (warps per lane quarter)
+    constexpr int WCOLS = GT / NCQ;                    // columns per warp
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int lq = warp & 3, cq = warp >> 2;
     const int r = lq * 32 + lane;  // tile row == TMEM lane
     const int64_t grow = row_base + r;
     const bool row_ok = INTERIOR || (grow >= p.row0 && grow < p.row1);
     const double na = (INTERIOR || grow < p.n) ? p.aux[grow] : 0.0;
-    const bool do_mirror = !DIAG && (p.flags & PO_FLAG_MIRROR) && row_base + GT <= col_base;
+    const bool do_mirror = DIAG || ((p.flags & PO_FLAG_MIRROR) && row_base + GT <= col_base);
     const int64_t ldx32 = (int64_t)p.nkb * GK;
-    constexpr int TP = DIAG ? (GT + 1) : 33;  // pitch of the staging buffer in elements
-    OUT_T* tbuf = DIAG ? reinterpret_cast<OUT_T*>(gsmem) + (size_t)r * TP + cq * 32
-                       : reinterpret_cast<OUT_T*>(gsmem) + (size_t)warp * (32 * 33) + (size_t)lane * TP;
-    // mirrored entry (c, r) of this thread's row r and tile column 0
-    OUT_T* mir_col0 = reinterpret_cast<OUT_T*>(p.mir) + (col_base - p.mir_row0) * p.ld_mir + (grow - p.mir_col0);
+    OUT_T* tbuf = reinterpret_cast<OUT_T*>(gsmem) + (size_t)warp * (32 * 33) + (size_t)lane * 33;
+    const OUT_T* wb = reinterpret_cast<const OUT_T*>(gsmem) + (size_t)warp * (32 * 33);
+    // where the transposed entries go: the mirror buffer, or (diagonal group) the group itself.
+    // mir_col0 = address of the mirrored entry (c, r) of this thread's row r and group column 0.
+    OUT_T* const mbase = DIAG ? reinterpret_cast<OUT_T*>(p.out) : reinterpret_cast<OUT_T*>(p.mir);
+    const int64_t m_ld = DIAG ? p.ld_out : p.ld_mir;
+    OUT_T* mir_col0 = mbase + (col_base - (DIAG ? p.out_row0 : p.mir_row0)) * m_ld + (grow - (DIAG ? p.out_col0 : p.mir_col0));
+    // a diagonal group's transposed entry (c, r) lies in ROW c, COLUMN r of the requested block
+    const bool mcol_ok = !DIAG || (grow >= p.col0 && grow < p.col1);
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        const int c0 = cq * 32 + half * 16;
-        uint32_t vh[16], vx[16], vy[16], vz[16];
-        const unsigned ta = tmem + ((unsigned)(lq * 32) << 16) + (unsigned)c0;
-        g_tmem_ld16(ta, vh);
-        g_tmem_ld16(ta + GT, vx);
-        if (MODE == GM_SC) {
-            g_tmem_ld16(ta + 2 * GT, vy);
-            g_tmem_ld16(ta + 3 * GT, vz);
-        }
-        g_tmem_wait_ld();
-        OUT_T val[16];
-        unsigned cancel = 0u;  // columns of this chunk whose Gram form cancelled too much
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const double nb = s_nb[c0 + j];
+    for (int blk = 0; blk < WCOLS / 32; ++blk) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int c0 = cq * WCOLS + blk * 32 + half * 16;
+            uint32_t vh[16], vx[16], vy[16], vz[16];
+            const unsigned ta = tmem + ((unsigned)(lq * 32) << 16) + (unsigned)c0;
+            g_tmem_ld16(ta, vh);
+            g_tmem_ld16(ta + GT, vx);
             if (MODE == GM_SC) {
-                // exact integer dot product of the centred doubled ranks, then 1 - rho as K_SC does
-                const long long t = 4096ll * (long long)__uint_as_float(vh[j]) +
-                                    64ll * ((long long)__uint_as_float(vx[j]) + (long long)__uint_as_float(vy[j])) +
-                                    (long long)__uint_as_float(vz[j]);
-                const double den = sqrt(na * nb);
-                const double v = (den == 0.0) ? __longlong_as_double(0x7FF8000000000000ll)  // scipy: NaN for a constant row
-                                              : 1.0 - (double)t / den;
-                val[j] = (OUT_T)v;
-                continue;
+                g_tmem_ld16(ta + 2 * GT, vy);
+                g_tmem_ld16(ta + 3 * GT, vz);
             }
-            const float dot = __uint_as_float(vh[j]) + __uint_as_float(vx[j]);
-            const double nsum = na + nb;
-            double d2 = nsum - 2.0 * (double)dot;
-            const bool on_diag = DIAG && r == c0 + j;
-            // a diagonal group recomputes for all its entries: the ones left of the diagonal are copies
-            const bool inside = DIAG ? (grow < p.n && col_base + c0 + j < p.n)
-                                     : (INTERIOR || (row_ok && col_base + c0 + j >= p.col0 && col_base + c0 + j < p.col1));
-            if (inside && !on_diag && d2 * 256.0 < nsum) cancel |= 1u << j;
-            d2 = (d2 > 0.0 ? d2 : 0.0) * GUNSCALE;
-            if (sizeof(OUT_T) == 8) val[j] = (OUT_T)sqrt(d2);
-            else val[j] = (OUT_T)sqrtf((float)d2);
-            if (on_diag) val[j] = (OUT_T)0;  // sklearn forces an exact zero diagonal
-        }
-        // exact recomputation, one entry at a time, by the whole warp
-        unsigned lanes = (MODE == GM_EUCL) ? __ballot_sync(0xFFFFFFFFu, cancel != 0u) : 0u;
-        while (lanes) {
-            const int l = __ffs(lanes) - 1;
-            lanes &= lanes - 1;
-            unsigned m = __shfl_sync(0xFFFFFFFFu, cancel, l);
-            const int64_t er = row_base + lq * 32 + l;
-            while (m) {
-                const int j = __ffs(m) - 1;
-                m &= m - 1;
-                const float* xa = p.X32 + er * ldx32;
-                const float* xb = p.X32 + (col_base + c0 + j) * ldx32;
-                double acc = 0.0;
-                for (int64_t k0 = 0; k0 < ldx32; k0 += 1024) {  // float32 partial sums of <= 32 terms per lane
-                    float part = 0.f;
-                    const int64_t k1 = min(ldx32, k0 + 1024);
-                    for (int64_t k = k0 + lane; k < k1; k += 32) {
-                        const float d = xa[k] - xb[k];
-                        part = fmaf(d, d, part);
-                    }
-                    acc += (double)part;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-                if (lane == l) {
-#pragma unroll
-                    for (int jj = 0; jj < 16; ++jj)
-                        if (jj == j) val[jj] = (sizeof(OUT_T) == 8) ? (OUT_T)sqrt(acc) : (OUT_T)sqrtf((float)acc);
-                }
-            }
-        }
-        if (do_mirror) {
-            OUT_T* mp = mir_col0 + (int64_t)c0 * p.ld_mir;
+            g_tmem_wait_ld();
+            OUT_T val[16];
+            unsigned cancel = 0u;  // columns of this chunk whose Gram form cancelled too much
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                if (INTERIOR || (row_ok && col_base + c0 + j >= p.col0 && col_base + c0 + j < p.col1)) *mp = val[j];
-                mp += p.ld_mir;
+                const double nb = s_nb[c0 + j];
+                if (MODE == GM_SC) {
+                    // exact integer dot product of the centred doubled ranks, then 1 - rho as K_SC does
+                    const long long t = 4096ll * (long long)__uint_as_float(vh[j]) +
+                                        64ll * ((long long)__uint_as_float(vx[j]) + (long long)__uint_as_float(vy[j])) +
+                                        (long long)__uint_as_float(vz[j]);
+                    const double den = sqrt(na * nb);
+                    const double v = (den == 0.0) ? __longlong_as_double(0x7FF8000000000000ll)  // scipy: NaN for a constant row
+                                                  : 1.0 - (double)t / den;
+                    val[j] = (OUT_T)v;
+                    continue;
+                }
+                const float dot = __uint_as_float(vh[j]) + __uint_as_float(vx[j]);
+                const double nsum = na + nb;
+                double d2 = nsum - 2.0 * (double)dot;
+                const bool on_diag = DIAG && r == c0 + j;
+                // a diagonal group recomputes for its entries right of the diagonal: the others are copies
+                const bool inside = DIAG ? (c0 + j > r && grow < p.n && col_base + c0 + j < p.n)
+                                         : (INTERIOR || (row_ok && col_base + c0 + j >= p.col0 && col_base + c0 + j < p.col1));
+                if (inside && d2 * 256.0 < nsum) cancel |= 1u << j;
+                d2 = (d2 > 0.0 ? d2 : 0.0) * GUNSCALE;
+                if (sizeof(OUT_T) == 8) val[j] = (OUT_T)sqrt(d2);
+                else val[j] = (OUT_T)sqrtf((float)d2);
+                if (on_diag) val[j] = (OUT_T)0;  // sklearn forces an exact zero diagonal
             }
-        }
+            // exact recomputation, one entry at a time, by the whole warp
+            unsigned lanes = (MODE == GM_EUCL) ? __ballot_sync(0xFFFFFFFFu, cancel != 0u) : 0u;
+            while (lanes) {
+                const int l = __ffs(lanes) - 1;
+                lanes &= lanes - 1;
+                unsigned m = __shfl_sync(0xFFFFFFFFu, cancel, l);
+                const int64_t er = row_base + lq * 32 + l;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float* xa = p.X32 + er * ldx32;
+                    const float* xb = p.X32 + (col_base + c0 + j) * ldx32;
+                    double acc = 0.0;
+                    for (int64_t k0 = 0; k0 < ldx32; k0 += 1024) {  // float32 partial sums of <= 32 terms per lane
+                        float part = 0.f;
+                        const int64_t k1 = min(ldx32, k0 + 1024);
+                        for (int64_t k = k0 + lane; k < k1; k += 32) {
+                            const float d = xa[k] - xb[k];
+                            part = fmaf(d, d, part);
+                        }
+                        acc += (double)part;
+                    }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) tbuf[half * 16 + j] = val[j];
-    }
-    if (DIAG) __syncthreads();  // every warp reads other warps' rows of the group below
-    else __syncwarp();
-    {
-        const int c = cq * 32 + lane;  // column of the group this lane stores
-        const int64_t gcol = col_base + c;
-        const bool col_ok = INTERIOR || (gcol >= p.col0 && gcol < p.col1);
-        const int64_t gr0 = row_base + lq * 32;
-        OUT_T* op = reinterpret_cast<OUT_T*>(p.out) + (gr0 - p.out_row0) * p.ld_out + (gcol - p.out_col0);
-        const OUT_T* dt = reinterpret_cast<const OUT_T*>(gsmem);
-        const OUT_T* wb = reinterpret_cast<const OUT_T*>(gsmem) + (size_t)warp * (32 * 33);
-#pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) {
-            OUT_T v;
-            if (DIAG) {
-                const int rw = lq * 32 + rr;
-                v = (c >= rw) ? dt[(size_t)rw * TP + c] : dt[(size_t)c * TP + rw];
-            } else {
-                v = wb[rr * 33 + lane];
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+                    if (lane == l) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj)
+                            if (jj == j) val[jj] = (sizeof(OUT_T) == 8) ? (OUT_T)sqrt(acc) : (OUT_T)sqrtf((float)acc);
+                    }
+                }
             }
-            if (INTERIOR || (col_ok && gr0 + rr >= p.row0 && gr0 + rr < p.row1)) *op = v;
-            op += p.ld_out;
+            if (do_mirror) {
+                OUT_T* mp = mir_col0 + (int64_t)c0 * m_ld;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    bool ok;
+                    if (DIAG) ok = c0 + j > r && mcol_ok && col_base + c0 + j >= p.row0 && col_base + c0 + j < p.row1;
+                    else ok = INTERIOR || (row_ok && col_base + c0 + j >= p.col0 && col_base + c0 + j < p.col1);
+                    if (ok) *mp = val[j];
+                    mp += m_ld;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) tbuf[half * 16 + j] = val[j];
         }
+        __syncwarp();
+        {
+            const int c = cq * WCOLS + blk * 32 + lane;  // column of the group this lane stores
+            const int64_t gcol = col_base + c;
+            const bool col_ok = INTERIOR || (gcol >= p.col0 && gcol < p.col1);
+            const int64_t gr0 = row_base + lq * 32;
+            OUT_T* op = reinterpret_cast<OUT_T*>(p.out) + (gr0 - p.out_row0) * p.ld_out + (gcol - p.out_col0);
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+                const OUT_T v = wb[rr * 33 + lane];
+                bool ok = INTERIOR || (col_ok && gr0 + rr >= p.row0 && gr0 + rr < p.row1);
+                if (DIAG) ok = ok && c >= lq * 32 + rr;  // on and right of the diagonal only
+                if (ok) *op = v;
+                op += p.ld_out;
+            }
+        }
+        __syncwarp();  // the staging block is rewritten by the next 32 columns
     }
 }
 
 template <typename OUT_T, int MODE>
-__global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams p) {
+__global__ void __launch_bounds__(GramCfg<MODE>::THREADS, GramCfg<MODE>::CTAS) gram_tile_kernel(const GramParams p) {
     using Cfg = GramCfg<MODE>;
     constexpr int NB = Cfg::NB, KS = Cfg::KS, NSTAGE = Cfg::STAGES;
     constexpr int SUB_BYTES = GT * KS * 2;               // one operand (hi or lo) of one 128-profile group per stage
@@ -525,8 +545,8 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
         g_mbar_init(accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {  // one warp allocates all 512 TMEM columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(&s_tmem)), "r"(512u));
+    if (warp == 0) {  // one warp allocates the CTA's TMEM columns (Eucl: 256, two CTAs share the SM's 512; SC: 512)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(&s_tmem)), "r"((unsigned)Cfg::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -642,7 +662,7 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_tile_kernel(const GramParams
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)Cfg::TMEM_COLS));
 }
 
 template <typename OUT_T, int MODE>
@@ -659,7 +679,7 @@ static int launch_gram_t(GramParams p, int64_t row1, int64_t col1, cudaStream_t 
     p.tiles_c = tc;
     const size_t smem = (size_t)Cfg::STAGES * (1 + Cfg::NB) * 2 * GT * Cfg::KS * 2 + 1024;
     PO_CUDA_CHECK(cudaFuncSetAttribute(gram_tile_kernel<OUT_T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gram_tile_kernel<OUT_T, MODE><<<dim3((unsigned)(tr * tc), 1, 1), GTHREADS, smem, stream>>>(p);
+    gram_tile_kernel<OUT_T, MODE><<<dim3((unsigned)(tr * tc), 1, 1), Cfg::THREADS, smem, stream>>>(p);
     return PO_OK;
 }
 

@@ -31,9 +31,24 @@
 // warp-uniform test: typically the pairs of one outlier profile of the tile), forms the
 // log-based value and adds the difference to the series value for exactly the terms with
 // u > 1/2 (G's polynomial is finite on [0, 1], so the provisional value is harmless).
-// The result of a pair depends only on that pair's data.  Dense profiles (4^k bins well
-// covered) need phase 2 in a few percent of the (warp, dimension) steps; sparse ones
-// (5 kb contigs at k = 5) need it almost always and run about 1.6x slower per term.
+// Dense profiles (4^k bins well covered) need phase 2 in a few percent of the (warp,
+// dimension) steps; sparse ones (5 kb contigs at k = 5) need it almost always and run
+// about 1.6x slower per term.
+//
+// Chunk variants.  Whether a chunk of 32 dimensions of a tile can meet u > 1/2 at all is known
+// before its loop starts: po_prepare_profiles stores, per group of 64 profiles and dimension, the
+// smallest and largest value of the group, and a pair (a, b) with max/min <= r has
+// u <= ((r-1)/(r+1))^2.  Per (tile, chunk) the warp evaluates the bound from the two groups' ranges
+// (one dimension per lane, loaded a chunk ahead) and runs one of three loops:
+//   V0  ratio <= 3   (u <= 1/4): degree-4 fit of G, no tracking of u, no phase 2   (10 FP32-pipe ops per term)
+//   V1  ratio <= 5.8 (u < 1/2): the degree-6 fit, no tracking, no phase 2          (12 ops)
+//   V2  anything else: the two-phase loop above.
+// The dimensions are permuted (the same permutation for every profile: a sum does not care) in
+// ascending order of their spread max/min over all profiles, so that the narrow dimensions share
+// chunks: at C2, 55 % of the (tile, chunk) pairs run V0 and 11 % V1, against 0 % and 18 % in the natural
+// order.  Both groups are the 64-aligned groups of the global profile index, for rows and columns
+// alike, so the variant of an entry (r, c) is that of (c, r) and does not depend on which call or tile
+// computes it: matrices stay bitwise symmetric and block rows equal the symmetric run bit for bit.
 #include "po_common.cuh"
 
 namespace po {
@@ -116,6 +131,15 @@ __device__ __forceinline__ float rcp_approx(float x) {
 #define JG1 1.666565838e-01f
 #define JG0 1.000000054e+00f
 
+// u in [0, 0.26]: degree-4 fit, relative error 7.0e-8 in exact arithmetic, 1.9e-7 in float32 Horner arithmetic
+#define JH4 3.614963273e-02f
+#define JH3 3.220779540e-02f
+#define JH2 6.700734910e-02f
+#define JH1 1.666553656e-01f
+#define JH0 1.000000059e+00f
+#define JSD_RATIO_V0 3.0f   // max/min <= 3   -> u <= 0.25
+#define JSD_RATIO_V1 5.8f   // max/min <= 5.8 -> u <= 0.4983 (the two-phase threshold is 1/2)
+
 __device__ __forceinline__ float jsd_G(float u) {
     float G = JG6;
     G = fmaf(G, u, JG5);
@@ -165,6 +189,8 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 struct JsdParams {
     const float* B;   // column-operand blocks  [n/64 groups][nchunks][32][64]
     const float* A;   // row-operand blocks     [n/32 groups][nchunks][32][32][2]
+    const float* gmin;  // [n/64 groups][nchunks * 32] smallest / largest value of the group per (permuted) dimension
+    const float* gmax;
     int nchunks;
     int64_t n;
     int64_t row0, row1, col0, col1;
@@ -176,6 +202,113 @@ struct JsdParams {
     int64_t ld_mir, mir_row0, mir_col0;
     unsigned flags;
 };
+
+// One chunk (32 dimensions) of a thread's 4 x 4 pairs, as 8 packed term pairs per dimension.
+// V = 0: degree-4 fit, u <= 1/4 guaranteed; V = 1: degree-6 fit, u < 1/2 guaranteed; V = 2: two phases.
+template <int V>
+__device__ __forceinline__ void jsd_chunk(const ulonglong2* __restrict__ sA, const ulonglong2* __restrict__ sB, u64 (&c2)[4][2]) {
+    const u64 g6 = pk2(JG6, JG6), g5 = pk2(JG5, JG5), g4 = pk2(JG4, JG4);
+    const u64 g3 = pk2(JG3, JG3), g2 = pk2(JG2, JG2), g1 = pk2(JG1, JG1), g0 = pk2(JG0, JG0);
+    const u64 h4 = pk2(JH4, JH4), h3 = pk2(JH3, JH3), h2 = pk2(JH2, JH2), h1 = pk2(JH1, JH1), h0 = pk2(JH0, JH0);
+#pragma unroll JUNROLL
+    for (int d = 0; d < JDK; ++d) {
+        const ulonglong2 A01 = sA[d * 16], A23 = sA[d * 16 + 1], Bv = sB[d * 16];
+        const u64 a2[4] = {A01.x, A01.y, A23.x, A23.y};
+        const u64 b2[2] = {Bv.x, Bv.y};
+        u64 dd[4][2], xx[4][2], uu[4][2];
+        float umax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const u64 sm = add2(a2[i], b2[j]);
+                dd[i][j] = sub2(a2[i], b2[j]);
+                float s0, s1;
+                upk2(sm, s0, s1);
+                xx[i][j] = mul2(dd[i][j], pk2(rcp_approx(s0), rcp_approx(s1)));
+                uu[i][j] = mul2(xx[i][j], xx[i][j]);
+                if (V == 2) {
+                    float u0, u1;
+                    upk2(uu[i][j], u0, u1);
+                    umax = fmaxf(umax, fmaxf(u0, u1));
+                }
+            }
+        u64 G[4][2];
+#define JSD_HORNER_FIRST(ga, gb)                  \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) \
+        _Pragma("unroll") for (int j = 0; j < 2; ++j) G[i][j] = fma2(ga, uu[i][j], gb);
+#define JSD_HORNER(gk)                            \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) \
+        _Pragma("unroll") for (int j = 0; j < 2; ++j) G[i][j] = fma2(G[i][j], uu[i][j], gk);
+        if (V == 0) {
+            JSD_HORNER_FIRST(h4, h3)
+            JSD_HORNER(h2)
+            JSD_HORNER(h1)
+            JSD_HORNER(h0)
+        } else {
+            JSD_HORNER_FIRST(g6, g5)
+            JSD_HORNER(g4)
+            JSD_HORNER(g3)
+            JSD_HORNER(g2)
+            JSD_HORNER(g1)
+            JSD_HORNER(g0)
+        }
+#undef JSD_HORNER
+#undef JSD_HORNER_FIRST
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) c2[i][j] = fma2(mul2(dd[i][j], xx[i][j]), G[i][j], c2[i][j]);
+
+        if (V == 2) {
+            // largest u of the warp's 512 terms in this dimension (u >= 0: bit order = value order)
+            const unsigned umax_w = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(umax));
+            if (umax_w > JSD_P2_BITS) {
+                // phase 2, packed: for the term pairs in which some lane met u > 1/2, form the log-based
+                // value s * fB(min(a,b)/s) and add (that - series value) where u > 1/2, 0 elsewhere.
+                // Typically a few of the 8 pairs are concerned (one outlier profile of the tile); sparse
+                // profiles flag all of them.
+                float a[4], b[4], dummy;
+                upk2(a2[0], a[0], dummy);
+                upk2(a2[1], a[1], dummy);
+                upk2(a2[2], a[2], dummy);
+                upk2(a2[3], a[3], dummy);
+                upk2(b2[0], b[0], b[1]);
+                upk2(b2[1], b[2], b[3]);
+                const u64 e4 = pk2(2.100300184e-01f, 2.100300184e-01f), e3 = pk2(3.274813073e-01f, 3.274813073e-01f);
+                const u64 e2 = pk2(1.000313256e+00f, 1.000313256e+00f), e1 = pk2(-2.000005795e+00f, -2.000005795e+00f);
+                const u64 e0 = pk2(1.386294378e+00f, 1.386294378e+00f), ln4 = pk2(1.386294361f, 1.386294361f);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float u0, u1;
+                        upk2(uu[i][j], u0, u1);
+#if JSD_BLOCK_P2
+                        if (!__any_sync(0xFFFFFFFFu, (u0 > 0.5f) | (u1 > 0.5f))) continue;
+#endif
+                        const u64 sm = add2(a2[i], b2[j]);
+                        float s0, s1;
+                        upk2(sm, s0, s1);  // 1/s again (same MUFU result as in phase 1) rather than 16 live registers
+                        const u64 v = mul2(pk2(fminf(a[i], b[2 * j]), fminf(a[i], b[2 * j + 1])),
+                                           pk2(rcp_approx(s0), rcp_approx(s1)));
+                        u64 E = fma2(e4, v, e3);
+                        E = fma2(E, v, e2);
+                        E = fma2(E, v, e1);
+                        E = fma2(E, v, e0);
+                        float v0, v1;
+                        upk2(v, v0, v1);
+                        const u64 fB = fma2(mul2(v, ln4), pk2(lg2_approx(v0), lg2_approx(v1)), E);
+                        const u64 series = mul2(mul2(dd[i][j], xx[i][j]), G[i][j]);
+                        const u64 delta = sub2(mul2(sm, fB), series);
+                        float d0, d1;
+                        upk2(delta, d0, d1);
+                        c2[i][j] = add2(c2[i][j], pk2(u0 > 0.5f ? d0 : 0.f, u1 > 0.5f ? d1 : 0.f));
+                    }
+            }
+        }
+    }
+}
 
 template <typename OUT_T>
 __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdParams p) {
@@ -221,8 +354,23 @@ __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdP
         for (int c = 0; c < JSTAGES && c < nchunks; ++c) issue(c);
     }
 
-    const u64 g6 = pk2(JG6, JG6), g5 = pk2(JG5, JG5), g4 = pk2(JG4, JG4);
-    const u64 g3 = pk2(JG3, JG3), g2 = pk2(JG2, JG2), g1 = pk2(JG1, JG1), g0 = pk2(JG0, JG0);
+    // variant of a chunk from the value ranges of the two 64-profile groups: one dimension per lane
+    const float* rI_min = p.gmin + (size_t)(row_base / 64) * nchunks * JDK + (tid & 31);
+    const float* rI_max = p.gmax + (size_t)(row_base / 64) * nchunks * JDK + (tid & 31);
+    const float* rJ_min = p.gmin + (size_t)(col_base / 64) * nchunks * JDK + (tid & 31);
+    const float* rJ_max = p.gmax + (size_t)(col_base / 64) * nchunks * JDK + (tid & 31);
+    auto lane_code = [&](int ch) -> unsigned {
+#ifdef JSD_FORCE_VARIANT
+        return JSD_FORCE_VARIANT;
+#else
+        const float ilo = rI_min[ch * JDK], ihi = rI_max[ch * JDK], jlo = rJ_min[ch * JDK], jhi = rJ_max[ch * JDK];
+        // a in [ilo, ihi], b in [jlo, jhi]: max(a/b, b/a) <= max(ihi/jlo, jhi/ilo)
+        if (ihi <= JSD_RATIO_V0 * jlo && jhi <= JSD_RATIO_V0 * ilo) return 0u;
+        if (ihi <= JSD_RATIO_V1 * jlo && jhi <= JSD_RATIO_V1 * ilo) return 1u;
+        return 2u;
+#endif
+    };
+    unsigned code_next = lane_code(0);
 
     u64 c2[4][2];
     double t[4][4];
@@ -236,102 +384,14 @@ __global__ void __launch_bounds__(JTHREADS, JSD_CTAS) jsd_tile_kernel(const JsdP
 
     for (int ch = 0; ch < nchunks; ++ch) {
         const int s = ch % JSTAGES;
+        const unsigned variant = __reduce_max_sync(0xFFFFFFFFu, code_next);
+        if (ch + 1 < nchunks) code_next = lane_code(ch + 1);  // in flight during this chunk's loop
         mbar_wait(bar0 + 8 * s, (unsigned)((ch / JSTAGES) & 1));
         const ulonglong2* sA = reinterpret_cast<const ulonglong2*>(jsmem + s * JSTAGE_BYTES) + 2 * ty;
         const ulonglong2* sB = reinterpret_cast<const ulonglong2*>(jsmem + s * JSTAGE_BYTES + JBLOCK_FLOATS * 4) + tx;
-#pragma unroll JUNROLL
-        for (int d = 0; d < JDK; ++d) {
-            const ulonglong2 A01 = sA[d * 16], A23 = sA[d * 16 + 1], Bv = sB[d * 16];
-            const u64 a2[4] = {A01.x, A01.y, A23.x, A23.y};
-            const u64 b2[2] = {Bv.x, Bv.y};
-            u64 dd[4][2], xx[4][2], uu[4][2];
-            float umax = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const u64 sm = add2(a2[i], b2[j]);
-                    dd[i][j] = sub2(a2[i], b2[j]);
-                    float s0, s1;
-                    upk2(sm, s0, s1);
-                    xx[i][j] = mul2(dd[i][j], pk2(rcp_approx(s0), rcp_approx(s1)));
-                    uu[i][j] = mul2(xx[i][j], xx[i][j]);
-                    float u0, u1;
-                    upk2(uu[i][j], u0, u1);
-                    umax = fmaxf(umax, fmaxf(u0, u1));
-                }
-            // largest u of the warp's 512 terms in this dimension (decides phase 2 below).  Choosing a
-            // lower-degree fit of G per (warp, dimension) from it was tried and measured slower: the extra
-            // warp-uniform branch splits the MUFU / FMA interleave of consecutive dimensions.
-            const unsigned umax_w = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(umax));  // u >= 0: bit order = value order
-            u64 G[4][2];
-#define JSD_HORNER_FIRST(ga, gb)                  \
-    _Pragma("unroll") for (int i = 0; i < 4; ++i) \
-        _Pragma("unroll") for (int j = 0; j < 2; ++j) G[i][j] = fma2(ga, uu[i][j], gb);
-#define JSD_HORNER(gk)                            \
-    _Pragma("unroll") for (int i = 0; i < 4; ++i) \
-        _Pragma("unroll") for (int j = 0; j < 2; ++j) G[i][j] = fma2(G[i][j], uu[i][j], gk);
-            {
-                JSD_HORNER_FIRST(g6, g5)
-                JSD_HORNER(g4)
-                JSD_HORNER(g3)
-                JSD_HORNER(g2)
-                JSD_HORNER(g1)
-                JSD_HORNER(g0)
-            }
-#undef JSD_HORNER
-#undef JSD_HORNER_FIRST
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) c2[i][j] = fma2(mul2(dd[i][j], xx[i][j]), G[i][j], c2[i][j]);
-
-#ifndef JSD_NO_PHASE2  /* timing experiments only: results are wrong where u > 1/2 */
-            if (umax_w > JSD_P2_BITS) {
-                // phase 2, packed: for the term pairs in which some lane met u > 1/2, form the log-based
-                // value s * fB(min(a,b)/s) and add (that - series value) where u > 1/2, 0 elsewhere.
-                // Typically a few of the 8 pairs are concerned (one outlier profile of the tile); sparse
-                // profiles flag all of them.
-                float a[4], b[4], dummy;
-                upk2(a2[0], a[0], dummy);
-                upk2(a2[1], a[1], dummy);
-                upk2(a2[2], a[2], dummy);
-                upk2(a2[3], a[3], dummy);
-                upk2(b2[0], b[0], b[1]);
-                upk2(b2[1], b[2], b[3]);
-                const u64 e4 = pk2(2.100300184e-01f, 2.100300184e-01f), e3 = pk2(3.274813073e-01f, 3.274813073e-01f);
-                const u64 e2 = pk2(1.000313256e+00f, 1.000313256e+00f), e1 = pk2(-2.000005795e+00f, -2.000005795e+00f);
-                const u64 e0 = pk2(1.386294378e+00f, 1.386294378e+00f), ln4 = pk2(1.386294361f, 1.386294361f);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        float u0, u1;
-                        upk2(uu[i][j], u0, u1);
-#if JSD_BLOCK_P2
-                        if (!__any_sync(0xFFFFFFFFu, (u0 > 0.5f) | (u1 > 0.5f))) continue;
-#endif
-                        const u64 sm = add2(a2[i], b2[j]);
-                        float s0, s1;
-                        upk2(sm, s0, s1);  // 1/s again (same MUFU result as in phase 1) rather than 16 live registers
-                        const u64 v = mul2(pk2(fminf(a[i], b[2 * j]), fminf(a[i], b[2 * j + 1])),
-                                           pk2(rcp_approx(s0), rcp_approx(s1)));
-                        u64 E = fma2(e4, v, e3);
-                        E = fma2(E, v, e2);
-                        E = fma2(E, v, e1);
-                        E = fma2(E, v, e0);
-                        float v0, v1;
-                        upk2(v, v0, v1);
-                        const u64 fB = fma2(mul2(v, ln4), pk2(lg2_approx(v0), lg2_approx(v1)), E);
-                        const u64 series = mul2(mul2(dd[i][j], xx[i][j]), G[i][j]);
-                        const u64 delta = sub2(mul2(sm, fB), series);
-                        float d0, d1;
-                        upk2(delta, d0, d1);
-                        c2[i][j] = add2(c2[i][j], pk2(u0 > 0.5f ? d0 : 0.f, u1 > 0.5f ? d1 : 0.f));
-                    }
-            }
-#endif
-        }
+        if (variant == 0u) jsd_chunk<0>(sA, sB, c2);
+        else if (variant == 1u) jsd_chunk<1>(sA, sB, c2);
+        else jsd_chunk<2>(sA, sB, c2);
         // fold the chunk's float32 partial sums (32 non-negative terms each) into float64
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -388,6 +448,8 @@ int launch_jsd(const void* d_P, int64_t n, int64_t dim, int64_t row0, int64_t ro
     JsdParams p;
     p.B = reinterpret_cast<const float*>(d_P);
     p.A = p.B + npad * ldp;
+    p.gmin = p.A + 2 * npad * ldp;
+    p.gmax = p.gmin + (npad / 64) * ldp;
     p.nchunks = (int)(ldp / JDK);
     p.n = n;
     p.row0 = row0; p.row1 = row1; p.col0 = col0; p.col1 = col1;

@@ -27,6 +27,8 @@
 
 namespace po {
 
+constexpr int JSD_MINMAX_SLICES = 64;  // row slices of the two-stage column min / max (fixed order: reproducible)
+
 int64_t prepared_row_elems(int metric, int64_t dim) {
     if (metric == PO_KT) {
         const int64_t nbits = dim * (dim - 1) / 2;
@@ -42,7 +44,12 @@ int64_t prepared_row_elems(int metric, int64_t dim) {
 // total bytes of the prepared operand buffer of n rows
 int64_t prepared_bytes(int metric, int64_t n, int64_t dim) {
     const int64_t ldp = prepared_row_elems(metric, dim);
-    if (metric == PO_JSD) return 3 * ((n + 63) / 64 * 64) * ldp * 4;  // blocked B + doubled A, rows padded to 64
+    if (metric == PO_JSD) {
+        // blocked B + doubled A (rows padded to 64), the per-group value ranges, the dimension permutation
+        // and the scratch of its computation (per-slice column minima / maxima, spreads)
+        const int64_t npad = (n + 63) / 64 * 64;
+        return 3 * npad * ldp * 4 + 2 * (npad / 64) * ldp * 4 + ldp * 4 + (2 * JSD_MINMAX_SLICES + 1) * ldp * 4;
+    }
     if (eucl_use_gram(metric, dim)) return gram_prepared_bytes(n, dim);
     if (sc_use_gram(metric, dim)) return sc_gram_prepared_bytes(n, dim);
     return n * ldp * 4;
@@ -89,33 +96,97 @@ __global__ void __launch_bounds__(256) prepare_copy_kernel(const void* __restric
 }
 
 
-// JSD: biased float32 profiles in the blocked layout of po_jsd.cu.  One CTA per
-// (group of 64 profiles, chunk of 32 dimensions); the transpose goes through shared memory.
+// JSD, step 1: smallest and largest (biased float32) value of every dimension over all profiles, in two
+// stages with a fixed order; step 2: spread = max / min per dimension; step 3: the permutation that
+// sorts the dimensions by ascending spread (ties by index; padding dimensions last).  po_jsd.cu runs a
+// cheaper loop on chunks of dimensions whose values are provably close together, and narrow dimensions
+// only share chunks when they are sorted; a sum over dimensions does not care about their order.
+template <typename T>
+__global__ void __launch_bounds__(256) jsd_colminmax_kernel(const void* __restrict__ X, int64_t n, int64_t dim, int64_t ldx,
+                                                            float* __restrict__ pmin, float* __restrict__ pmax, int64_t ldp) {
+    const int64_t col = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (col >= dim) return;
+    const int64_t rows_per = (n + JSD_MINMAX_SLICES - 1) / JSD_MINMAX_SLICES;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
+    float lo = __int_as_float(0x7F800000), hi = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+        const float v = (float)load_as_double<T>(X, r * ldx + col) + 1e-30f;
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+    pmin[(int64_t)blockIdx.y * ldp + col] = lo;
+    pmax[(int64_t)blockIdx.y * ldp + col] = hi;
+}
+
+__global__ void __launch_bounds__(256) jsd_spread_kernel(const float* __restrict__ pmin, const float* __restrict__ pmax,
+                                                         int64_t dim, int64_t ldp, float* __restrict__ spread) {
+    const int64_t col = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (col >= ldp) return;
+    float sp = __int_as_float(0x7F800000);  // padding dimensions sort last
+    if (col < dim) {
+        float lo = __int_as_float(0x7F800000), hi = 0.f;
+        for (int y = 0; y < JSD_MINMAX_SLICES; ++y) {
+            lo = fminf(lo, pmin[(int64_t)y * ldp + col]);
+            hi = fmaxf(hi, pmax[(int64_t)y * ldp + col]);
+        }
+        sp = hi / lo;
+        if (!(sp == sp)) sp = __int_as_float(0x7F800000);  // NaN profiles: keep the order total
+    }
+    spread[col] = sp;
+}
+
+__global__ void __launch_bounds__(256) jsd_rank_kernel(const float* __restrict__ spread, int64_t ldp, int* __restrict__ perm) {
+    const int64_t d = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (d >= ldp) return;
+    const float mine = spread[d];
+    int64_t before = 0;
+    for (int64_t e = 0; e < ldp; ++e) {
+        const float v = spread[e];
+        before += (v < mine) || (v == mine && e < d);
+    }
+    perm[before] = (int)d;
+}
+
+// JSD: biased float32 profiles in the blocked layout of po_jsd.cu, dimensions permuted.  One CTA per
+// (group of 64 profiles, chunk of 32 dimensions); the transpose goes through shared memory.  Also the
+// smallest and largest value of the group per dimension (profiles beyond n do not count: their tiles'
+// results are never stored).
 template <typename T>
 __global__ void __launch_bounds__(256) prepare_jsd_kernel(const void* __restrict__ X, int64_t n, int64_t dim,
                                                           int64_t ldx, float* __restrict__ PB, float* __restrict__ PA,
-                                                          int nchunks) {
+                                                          int nchunks, const int* __restrict__ perm,
+                                                          float* __restrict__ gmin, float* __restrict__ gmax) {
     __shared__ float tile[64][33];
     const int64_t grp = blockIdx.x;
     const int kc = blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t e = perm[(int64_t)kc * 32 + lane];  // source dimension of this lane's column
     for (int r = w; r < 64; r += 8) {
         const int64_t row = grp * 64 + r;
-        const int64_t e = (int64_t)kc * 32 + lane;
         float v = 0.f;
         if (row < n && e < dim) v = (float)load_as_double<T>(X, row * ldx + e);
         tile[r][lane] = v + 1e-30f;
     }
     __syncthreads();
     float* blkB = PB + ((size_t)grp * nchunks + kc) * 2048;
-    for (int e = threadIdx.x; e < 2048; e += 256) blkB[e] = tile[e & 63][e >> 6];  // [d][c]
+    for (int q = threadIdx.x; q < 2048; q += 256) blkB[q] = tile[q & 63][q >> 6];  // [d][c]
     // two row-operand blocks (profiles 0..31 and 32..63 of the group): [d][r][2]
     for (int h = 0; h < 2; ++h) {
         float2* blkA = reinterpret_cast<float2*>(PA + ((size_t)(grp * 2 + h) * nchunks + kc) * 2048);
-        for (int e = threadIdx.x; e < 1024; e += 256) {
-            const float v = tile[h * 32 + (e & 31)][e >> 5];
-            blkA[e] = make_float2(v, v);
+        for (int q = threadIdx.x; q < 1024; q += 256) {
+            const float v = tile[h * 32 + (q & 31)][q >> 5];
+            blkA[q] = make_float2(v, v);
         }
+    }
+    if (w == 0) {
+        float lo = __int_as_float(0x7F800000), hi = 0.f;
+        const int64_t rows = min((int64_t)64, n - grp * 64);
+        for (int r = 0; r < rows; ++r) {
+            lo = fminf(lo, tile[r][lane]);
+            hi = fmaxf(hi, tile[r][lane]);
+        }
+        gmin[((size_t)grp * nchunks + kc) * 32 + lane] = lo;
+        gmax[((size_t)grp * nchunks + kc) * 32 + lane] = hi;
     }
 }
 
@@ -226,8 +297,24 @@ static int launch_prepare_t(int metric, const void* d_X, int64_t n, int64_t dim,
             const int64_t npad = (n + 63) / 64 * 64;
             float* PB = (float*)d_P;
             float* PA = PB + npad * ldp;
+            float* gmin = PA + 2 * npad * ldp;
+            float* gmax = gmin + (npad / 64) * ldp;
+            int* perm = reinterpret_cast<int*>(gmax + (npad / 64) * ldp);
+            float* pmin = reinterpret_cast<float*>(perm + ldp);
+            float* pmax = pmin + (int64_t)JSD_MINMAX_SLICES * ldp;
+            float* spread = pmax + (int64_t)JSD_MINMAX_SLICES * ldp;
+            dim3 g1((unsigned)((dim + 255) / 256), JSD_MINMAX_SLICES, 1);
+            jsd_colminmax_kernel<T><<<g1, 256, 0, stream>>>(d_X, n, dim, ldx, pmin, pmax, ldp);
+            count_launch(2);
+            PO_LAUNCH_CHECK("jsd_colminmax_kernel");
+            jsd_spread_kernel<<<(unsigned)((ldp + 255) / 256), 256, 0, stream>>>(pmin, pmax, dim, ldp, spread);
+            count_launch(2);
+            PO_LAUNCH_CHECK("jsd_spread_kernel");
+            jsd_rank_kernel<<<(unsigned)((ldp + 255) / 256), 256, 0, stream>>>(spread, ldp, perm);
+            count_launch(2);
+            PO_LAUNCH_CHECK("jsd_rank_kernel");
             dim3 g((unsigned)(npad / 64), (unsigned)nchunks, 1);
-            prepare_jsd_kernel<T><<<g, 256, 0, stream>>>(d_X, n, dim, ldx, PB, PA, nchunks);
+            prepare_jsd_kernel<T><<<g, 256, 0, stream>>>(d_X, n, dim, ldx, PB, PA, nchunks, perm, gmin, gmax);
             count_launch(2);
             PO_LAUNCH_CHECK("prepare_jsd_kernel");
             return PO_OK;
