@@ -642,9 +642,10 @@ __global__ void __launch_bounds__(GramCfg<MODE>::THREADS, GramCfg<MODE>::CTAS) g
         const int64_t gc = col_base + tid;
         s_nb[tid] = (gc < p.n) ? p.aux[gc] : 0.0;
     }
-    __syncthreads();
+    // the warps that do not drive the pipeline sleep on the accumulators' mbarrier (not on a CTA barrier)
     g_mbar_wait(accum, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();  // s_nb is visible
 #pragma unroll
     for (int g = 0; g < NB; ++g) {
         if (!act[g]) continue;

@@ -123,7 +123,11 @@ def _adversarial_sequences(rng):
 @pytest.mark.parametrize("kernel", ["auto", "general"])
 @pytest.mark.parametrize("pattern,strand", [("1111", "both"), ("1111", "minus"), ("11111", "plus"),
                                             ("111010011", "plus"), ("1101011", "both"), ("1" * 6, "both"),
-                                            ("1001", "both"), ("10101", "minus")])
+                                            ("1001", "both"), ("10101", "minus"),
+                                            # patterns that are not their own mirror image: minus-strand words from the
+                                            # reverse-complement register of the segment kernel
+                                            ("111010011", "both"), ("111010011", "minus"), ("110101", "minus"),
+                                            ("1101", "both"), ("1100000000000001", "both")])
 def test_irregular_fasta_layouts(kernel, pattern, strand, monkeypatch):
     """Line-segment fast path against the oracle on layouts that break its assumptions:
     random line widths, widths below/at/above the segment limits, CRLF, blank lines,
