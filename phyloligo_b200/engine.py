@@ -209,7 +209,7 @@ def prepare(X, metric):
     n, dim = int(X.shape[0]), int(X.shape[1])
     total = lib.po_prepared_bytes(METRICS[metric], n, dim)
     _lib.check(total, "po_prepared_bytes")
-    free, _ = torch.cuda.mem_get_info()
+    free = torch.cuda.mem_get_info()[0] if total >= (4 << 30) else total  # only worth a driver call for large operands
     if total > free:
         hint = (" (KT keeps two bit planes over the dim(dim-1)/2 element pairs of every profile: %.1f MB per "
                 "profile at dim = %d)" % (total / max(1, n) / 1e6, dim)) if metric == "KT" else ""
