@@ -294,6 +294,35 @@ int po_host_pread(int fd, int64_t file_offset, void* h_dst, int64_t bytes, int t
 int po_host_transpose_f32(float* h_dst, int64_t ld_dst, const float* h_src, int64_t ld_src, int64_t rows,
                           int64_t cols, int threads);
 
+/*
+ * The front half of phyloselect.py (bin/phyloselect.py) on the device: what its K-medoids loop and
+ * its nearest-neighbour consumers read out of the N x N matrix, while the matrix (or a block row of it,
+ * [n_rows x n_cols] with row pitch ld, PO_F32 or PO_F64) is resident in device memory.
+ *   po_matrix_rowsums      d_out[i] = sum_j D[row(i), j] in float64 -- np.sum(D, axis=1) of the medoid
+ *                          heuristic (:291-309); row(i) = d_rows[i] or i when d_rows is NULL.  With
+ *                          d_labels (int32 per column) and d_row_labels (int32 per output row) the sum
+ *                          runs over the columns j with d_labels[j] == d_row_labels[i] only: the
+ *                          within-cluster cost of every member and of the current medoids (:197-240)
+ *   po_matrix_argmin_rows  d_out[j] = argmin_c D[d_rows[c], j], first minimum on ties --
+ *                          np.argmin(D[medoid_ics, :], axis=0) (:187-195)
+ *   po_cluster_argmin      per cluster c < k: d_count[c] members, d_best_cost[c] = the smallest d_cost
+ *                          among them and d_best_idx[c] = the first member that has it (-1 for an empty
+ *                          cluster) -- np.argmin(all_costs) over the members in index order (:224-227);
+ *                          d_work: 16 k bytes of scratch
+ *   po_matrix_knn          the k (<= 1024) nearest neighbours of every row, ascending distance, ties by
+ *                          column, the row's own column (self0 + i) excluded -- what sklearn's
+ *                          kneighbors_graph(mode="distance") gives TSNE / HDBSCAN on a precomputed matrix
+ *                          (:381-428); d_idx int32 [n_rows x k], d_dist float32 [n_rows x k]
+ */
+int po_matrix_rowsums(const void* d_D, int64_t ld, int dtype, const int64_t* d_rows, int64_t n_rows, int64_t n_cols,
+                      const int* d_labels, const int* d_row_labels, double* d_out, po_stream_t stream);
+int po_matrix_argmin_rows(const void* d_D, int64_t ld, int dtype, const int64_t* d_rows, int k, int64_t n_cols, int* d_out,
+                          po_stream_t stream);
+int po_cluster_argmin(const double* d_cost, const int* d_labels, int64_t n, int k, void* d_work, int64_t* d_best_idx,
+                      double* d_best_cost, int64_t* d_count, po_stream_t stream);
+int po_matrix_knn(const void* d_D, int64_t ld, int dtype, int64_t n_rows, int64_t n_cols, int64_t self0, int k, int* d_idx,
+                  float* d_dist, po_stream_t stream);
+
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
 int64_t po_launch_count(void);
 

@@ -28,7 +28,8 @@ EXPORTED = [
     "po_profile_batch", "po_prepared_row_bytes", "po_prepared_bytes", "po_prepare_profiles", "po_rank_transform", "po_distance_block", "po_distance_block_ex",
     "po_ipc_export", "po_ipc_open", "po_ipc_close", "po_savetxt_host", "po_copy2d_async", "po_window_count_byte", "po_window_distances",
     "po_host_prefault", "po_host_register", "po_host_unregister", "po_host_copy2d", "po_host_pwrite2d",
-    "po_host_pread", "po_host_transpose_f32", "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read", "po_microbench",
+    "po_host_pread", "po_host_transpose_f32",
+    "po_matrix_rowsums", "po_matrix_argmin_rows", "po_cluster_argmin", "po_matrix_knn", "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read", "po_microbench",
 ]
 
 
@@ -104,6 +105,14 @@ def load():
     lib.po_host_pread.restype = i32
     lib.po_host_transpose_f32.argtypes = [vp, i64, vp, i64, i64, i64, i32]
     lib.po_host_transpose_f32.restype = i32
+    lib.po_matrix_rowsums.argtypes = [vp, i64, i32, vp, i64, i64, vp, vp, vp, vp]
+    lib.po_matrix_rowsums.restype = i32
+    lib.po_matrix_argmin_rows.argtypes = [vp, i64, i32, vp, i32, i64, vp, vp]
+    lib.po_matrix_argmin_rows.restype = i32
+    lib.po_cluster_argmin.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp]
+    lib.po_cluster_argmin.restype = i32
+    lib.po_matrix_knn.argtypes = [vp, i64, i32, i64, i64, i64, i32, vp, vp, vp]
+    lib.po_matrix_knn.restype = i32
     lib.po_launch_count.restype = i64
     lib.po_timing_enable.argtypes = [i32]
     lib.po_timing_enable.restype = i32
