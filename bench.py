@@ -415,6 +415,47 @@ def run_extra_configs(device, scale, hbm_peak, bf16_peak, fp32_peak):
     return extras
 
 
+def run_select_leg(matrix, hbm_peak):
+    """phyloselect's front half on the matrix that is resident after a step: the
+    K-medoids loop of bin/phyloselect.py:119-240 and the neighbour graph of its TSNE / HDBSCAN consumers
+    (:381-428; default perplexity 100 -> 301 neighbours), all single passes over the N x N matrix in HBM."""
+    import torch
+    from phyloligo_b200 import phyloselect
+
+    n = int(matrix.shape[0])
+    nbytes = n * n * 4
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, out
+
+    ms_sum, _ = timed(lambda: phyloselect.row_sums(matrix))
+    t0 = time.perf_counter()
+    km = phyloselect.KMedoids(n_clusters=2).fit(matrix)
+    torch.cuda.synchronize()
+    fit_s = time.perf_counter() - t0
+    k = min(301, n - 1)
+    ms_knn, _ = timed(lambda: phyloselect.knn_graph(matrix, k), reps=1)
+    return {
+        "matrix": "%d x %d float32, resident after the distance stage" % (n, n),
+        "row_sums_ms": ms_sum,
+        "row_sums_roofline": {"bound": "hbm", "achieved": nbytes / (ms_sum * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": nbytes / (ms_sum * 1e-3) / 1e9 / hbm_peak},
+        "kmedoids": {"n_clusters": 2, "iterations": int(km.n_iter_), "seconds": fit_s,
+                     "cluster_sizes": np.bincount(km.labels_, minlength=2).tolist(),
+                     "passes_over_the_matrix": 1 + int(km.n_iter_), "note": "heuristic initialisation + one masked pass per iteration"},
+        "knn": {"k": k, "ms": ms_knn, "gbytes_per_s_one_pass_equivalent": nbytes / (ms_knn * 1e-3) / 1e9,
+                "note": "radix select: four histogram passes + one gather pass over every row"},
+    }
+
+
 def run_cli_leg(fasta, n_contigs, pairs_unique, rank, world, device, want_rows):
     """The call a user of the reference makes: phyloligo.compute_frequencies(...) then
     phyloligo.compute_distances("joblib", "memmap", ...) (reference bin/phyloligo.py:980-997, 536-553)
@@ -746,6 +787,15 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(io_bytes, op=dist.ReduceOp.SUM)
 
+    select_leg = None
+    if world == 1 and not args.no_extra:
+        try:
+            hbm_for_select = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+        except Exception:
+            hbm_for_select = 6650.0
+        step_resident()  # the matrix of a fresh step
+        select_leg = run_select_leg(matrix, hbm_for_select)
+
     # ---- the drop-in path itself: compute_frequencies + compute_distances(... "memmap" ...) into a real file ----
     e2e_cli = None
     peer_exchange = job is not None and job.peers is not None
@@ -828,7 +878,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_extra:
             bf16_peak = float(peaks.get("bf16_tflops", 1665.5))
-            line["extra"] = {"configs": run_extra_configs(device, args.scale, hbm_peak, bf16_peak, fp32_peak),
+            line["extra"] = {"select": select_leg,
+                             "configs": run_extra_configs(device, args.scale, hbm_peak, bf16_peak, fp32_peak),
                              "peaks": {"hbm_gbs": hbm_peak, "bf16_tflops_burst": bf16_peak, "fp32_ffma_tflops": fp32_peak,
                                        "source": "MEASURED_PEAKS.json (HBM, bf16 burst); po_microbench in this run (FP32, POPC)"}}
         if world == 1 and not args.no_cpu_baseline:

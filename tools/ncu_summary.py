@@ -1,26 +1,12 @@
-#!/usr/bin/env python3
-"""Print the metrics we track from an .ncu-rep (raw page): python tools/ncu_summary.py rep [kernel-substring]"""
-import csv, subprocess, sys
-rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
-hdr, units = rows[0], rows[1]
-KEYS = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers",
-        "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
-        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
-        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.avg"]
-for r in rows[2:]:
-    name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else ""
-    if len(sys.argv) > 2 and sys.argv[2] not in name:
-        continue
-    print("==", name[:100])
-    for h, u, v in zip(hdr, units, r):
-        if h in KEYS[1:]:
-            print("  %-70s %-10s %s" % (h, u, v))
-    stalls = [(float(v), h) for h, v in zip(hdr, r) if "issue_stalled" in h and h.endswith("per_issue_active.ratio")]
-    for v, h in sorted(stalls, reverse=True)[:8]:
-        print("  stall %-64s %.3f" % (h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""), v))
+import csv,sys,subprocess
+f=sys.argv[1]
+out=subprocess.run(["ncu","-i",f,"--page","raw","--csv"],capture_output=True,text=True).stdout
+rows=list(csv.reader(out.splitlines()))
+hdr,units,vals=rows[0],rows[1],rows[2]
+d={h:(v,u) for h,u,v in zip(hdr,units,vals)}
+keys=["Kernel Name","gpu__time_duration.sum","launch__grid_size","launch__block_size","launch__registers_per_thread","launch__shared_mem_per_block_dynamic","launch__occupancy_limit_shared_mem","launch__occupancy_limit_registers","launch__occupancy_limit_warps","sm__warps_active.avg.pct_of_peak_sustained_active","dram__bytes_read.sum","dram__bytes_write.sum","gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed","sm__throughput.avg.pct_of_peak_sustained_elapsed","smsp__issue_active.avg.pct_of_peak_sustained_active","sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active","sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active","sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active","sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active","sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active","sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active","sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active","sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active","sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active","sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active","sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active","smsp__warps_eligible.avg.per_cycle_active","smsp__inst_executed.sum","l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum","l1tex__data_pipe_lsu_wavefronts_mem_shared.sum","lts__t_bytes.sum","smsp__average_warp_latency_issue_stalled_barrier.ratio","smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
+for k in keys:
+    if k in d: print("%-80s %s %s"%(k,d[k][0],d[k][1]))
+# stall reasons
+st=[(float(v.replace(',','')),h) for h,(v,u) in d.items() if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and v not in ("","n/a")]
+for v,h in sorted(st,reverse=True)[:7]: print("  stall %-60s %.2f"%(h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")],v))
