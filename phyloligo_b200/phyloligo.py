@@ -376,7 +376,7 @@ def _my_row_ranges(n, rank, world):
     return [ranges[i] for i in sharding.owned_ranges(ranges, rank, world) if ranges[i][1] > ranges[i][0]]
 
 
-def _open_file_matrix(path, n, offset=0, create=True):
+def _open_file_matrix(path, n, offset=0, create=True, fresh=None):
     """The output region as a hostsink.FileMatrix whose pages (of this rank's rows) are being instantiated.
     Rank 0 creates the file, the others attach after the barrier."""
     rank, world = ranks()
@@ -390,8 +390,10 @@ def _open_file_matrix(path, n, offset=0, create=True):
     _barrier()
     if rank != 0:
         fm = hostsink.FileMatrix(path, n, n, np.float32, offset, create=False)
+    # rank 0 knows whether the file's pages exist already
+    fresh = fresh if fresh is not None else _broadcast_str(fm.fresh if rank == 0 else None)
     threads = hostsink.host_threads(world)
-    fm.warm(_my_row_ranges(n, rank, world), threads=max(1, min(4, threads // 2)))
+    fm.warm(_my_row_ranges(n, rank, world), threads=max(1, min(4, threads // 2)), fresh=bool(fresh))
     return fm
 
 
@@ -499,7 +501,7 @@ def compute_distances_h5py(freq_name, dist_name, metric="Eucl"):
         _, _, offset = io_formats.dataset_location(dist_name, "distances")
     else:
         offset = fm.offset
-    fm = _open_file_matrix(dist_name, n, offset, create=False)
+    fm = _open_file_matrix(dist_name, n, offset, create=False, fresh=True)  # the writer has just truncated the file to size
     try:
         _fill_host_matrix(fm.array, _profiles_to_device(freqs), _large_metric(metric))
     finally:
@@ -553,6 +555,7 @@ def _prepare_outputs(params):
         offset = writer.data_off
         writer.close()
         fm = hostsink.FileMatrix(params.out_file, n, n, np.float32, offset, create=False)
+        fm.fresh = True
     else:
         return
     fm.warm([(0, n)], threads=max(1, min(4, threads // 2)))
