@@ -205,9 +205,9 @@ def cpu_c_port_rates(seqs_sample, n_profile, n_dist, threads):
 
 def ncu_traffic(n_contigs):
     """DRAM bytes per launch of the JSD tile kernel from the committed ncu --set full captures
-    (profiles/r01_traffic.json), when one was taken at this problem size; else None."""
+    (profiles/r02_traffic.json), when one was taken at this problem size; else None."""
     try:
-        recs = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["jsd_tile_kernel"]
+        recs = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["jsd_tile_kernel"]
         for rec in recs if isinstance(recs, list) else [recs]:
             if rec["n_contigs"] == n_contigs:
                 return rec["dram_bytes_per_launch"]
