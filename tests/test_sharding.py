@@ -119,12 +119,36 @@ def _block_rows_worker(rank, world, port, n, dim):
             job = multigpu.BlockRows(n, torch.float64, rank, world, exchange="nccl", device=torch.device("cpu"))
             job.matrix.fill_(float("nan"))
             job.compute("Eucl", None, None, dim)
+            first_pass = list(calls)
+            # the command line's sink: every finished block is handed to `ship` exactly once, right parts of a
+            # block row before the closing exchange, left parts after it; together they tile the rank's rows
+            shipped = torch.full((n, n), float("nan"), dtype=torch.float64)
+            order = []
+
+            def ship(block, row0, col0):
+                assert torch.isnan(shipped[row0:row0 + block.shape[0], col0:col0 + block.shape[1]]).all()
+                shipped[row0:row0 + block.shape[0], col0:col0 + block.shape[1]] = block
+                order.append((row0, col0))
+
+            job.compute("Eucl", None, None, dim, ship=ship)
         finally:
             engine.distance_block = keep
+        for i in job.my_ranges:
+            a, b = job.ranges[i]
+            assert torch.equal(shipped[a:b], full[a:b]), "rank %d shipped rows of block row %d" % (rank, i)
+        owned = torch.zeros(n, dtype=torch.bool)
+        for i in job.my_ranges:
+            owned[job.ranges[i][0]:job.ranges[i][1]] = True
+        assert torch.isnan(shipped[~owned]).all()
+        rights = [k for k, (r0, c0) in enumerate(order) if c0 == r0]
+        lefts = [k for k, (r0, c0) in enumerate(order) if c0 == 0 and r0 > 0]
+        assert len(rights) == len(job.my_ranges) and (not lefts or max(rights) < min(lefts))
         for i, rows in job.out_rows.items():
             a, b = job.ranges[i]
             assert torch.equal(rows, full[a:b]), "rank %d block row %d" % (rank, i)
         # every unordered pair of blocks is computed by exactly one rank: upper-triangle area only
+        assert calls[len(first_pass):] == first_pass  # shipping does not change what is launched
+        calls = first_pass
         mine = sum((r1 - r0) * (c1 - c0) for r0, r1, c0, c1 in calls)
         diag = sum((r1 - r0) ** 2 for r0, r1, c0, c1 in calls if (r0, r1) == (c0, c1))
         assert mine - diag + (diag + sum(r1 - r0 for r0, r1, c0, c1 in calls if (r0, r1) == (c0, c1))) // 2 == job.upper_area()
