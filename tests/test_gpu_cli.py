@@ -85,3 +85,42 @@ def test_bad_strand_exits_like_the_reference(fasta, capsys):
         phyloligo.compute_frequency("ACGT", "1111", "sideways")
     assert e.value.code == 1
     assert "strand parameter" in capsys.readouterr().err
+
+
+def test_command_line_against_the_unmodified_reference_script(tmp_path):
+    """Every mode of the reference's own bin/phyloligo.py that runs in the build container (eleven runs through
+    oracle/run_reference_cli.py, committed as tests/golden/cli_golden.npz) against this command line on the
+    same assembly with the same arguments: the -q frequency files bit for bit, the matrices within the
+    tolerances of BASELINE.json (1e-6; 1e-4 for the tensor-core Eucl of the --large modes)."""
+    import sys
+    from conftest import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import make_cli_golden as mk
+    golden = dict(np.load(os.path.join(GOLDEN, "cli_golden.npz")))
+    fasta, n = mk.assembly()
+    path = os.path.join(tmp_path, "asm.fasta")
+    open(path, "wb").write(fasta)
+    for name in golden["names"]:
+        args = str(golden[name + "_args"]).split()
+        large = args[args.index("--large") + 1] if "--large" in args else "None"
+        metric = args[args.index("-d") + 1]
+        out, freq = os.path.join(tmp_path, name + ".mat"), os.path.join(tmp_path, name + ".freq")
+        phyloligo.main(["-i", path, "-o", out, "-q", freq, "-w", str(tmp_path)] + args)
+        ref_M, ref_F = golden[name + "_matrix"], golden[name + "_freq"]
+        F = np.loadtxt(freq)
+        assert np.array_equal(F, ref_F), name  # the text the reference wrote, value for value
+        got = np.loadtxt(out) if large == "None" else io_formats.read_memmap(out)
+        assert got.shape == ref_M.shape and got.dtype == ref_M.dtype, name
+        assert np.array_equal(np.isnan(got), np.isnan(ref_M)), name
+        m = ~np.isnan(ref_M)
+        if metric == "KT":
+            tol, atol = 1e-12, 1e-12
+        elif large != "None":
+            # both sides compute in float32 here: the reference's own rounding (sklearn's float32 Gram form,
+            # the broadcast float32 JSD) is part of the difference
+            tol, atol = (1e-4, 1e-6) if metric == "Eucl" else (5e-6, 1e-7)
+        else:
+            tol, atol = 1e-6, 1e-12
+        assert np.allclose(got[m], ref_M[m], rtol=tol, atol=atol), (name, np.abs(got[m] - ref_M[m]).max())
+        # the reference's own acceptance threshold between its modes (bin/phyloligo_comparemat.py:44)
+        assert np.allclose(np.nan_to_num(got), np.nan_to_num(ref_M), atol=1e-3), name
