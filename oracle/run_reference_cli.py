@@ -20,8 +20,14 @@ executes the script with ``runpy`` -- every line of the reference itself runs as
                              parity unpinned, see there)
   h5py                       absent: the --large h5py mode cannot be run here
 
+  matplotlib, hdbscan        empty modules (imported at the top of bin/phyloselect.py; plotting, t-SNE and
+                             HDBSCAN are not exercised: `-m kmedoids` without `-t`)
+  Bio.SeqIO.write            FASTA writer as Biopython's: ">" + title line, sequence wrapped at 60 columns
+
+``--script phyloselect.py`` (first argument) runs another script of phylopackage/bin the same way.
 Nothing of the reference is copied; it is read where it lies.  Used by tests/golden/make_cli_golden.py
-to produce the committed end-to-end fixtures (the GPU box has no /root/reference).
+and make_select_cli_golden.py to produce the committed end-to-end fixtures (the GPU box has no
+/root/reference).
 """
 import os
 import runpy
@@ -105,6 +111,19 @@ def install_shims():
     bio = types.ModuleType("Bio")
     seqio = types.ModuleType("Bio.SeqIO")
     seqio.parse = _parse
+
+    def _write(records, handle, fmt):
+        assert fmt == "fasta"
+        count = 0
+        for rec in records:
+            handle.write(">%s\n" % rec.description)
+            seq = str(rec.seq)
+            for p in range(0, len(seq), 60):
+                handle.write(seq[p:p + 60] + "\n")
+            count += 1
+        return count
+
+    seqio.write = _write
     seqmod = types.ModuleType("Bio.Seq")
     seqmod.Seq = Seq
     cluster = types.ModuleType("Bio.Cluster")
@@ -124,19 +143,35 @@ def install_shims():
             import h5py  # noqa: F401
         except ImportError:
             sys.modules["h5py"] = types.ModuleType("h5py")  # imported at the top of the script, used by --large h5py only
+    for name in ("matplotlib", "matplotlib.pyplot", "hdbscan"):  # top-level imports of bin/phyloselect.py
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except ImportError:
+                mod = types.ModuleType(name)
+                mod.use = lambda *a, **k: None
+                sys.modules[name] = mod
+    if "matplotlib.pyplot" in sys.modules and not hasattr(sys.modules["matplotlib"], "pyplot"):
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)  # `from phylopackage import phylodist`
 
 
 def run(argv):
-    """Execute the reference script with the given command-line arguments (list of str)."""
-    if not os.path.isfile(SCRIPT):
+    """Execute a reference script (default bin/phyloligo.py; ``--script NAME`` first selects another one of
+    phylopackage/bin) with the given command-line arguments (list of str)."""
+    argv = list(argv)
+    script = SCRIPT
+    if argv[:1] == ["--script"]:
+        script = os.path.join(REFERENCE_ROOT, "phylopackage", "bin", argv[1])
+        argv = argv[2:]
+    if not os.path.isfile(script):
         raise RuntimeError("reference checkout not mounted at %s" % REFERENCE_ROOT)
     install_shims()
     old = sys.argv
-    sys.argv = [SCRIPT] + list(argv)
+    sys.argv = [script] + argv
     try:
-        runpy.run_path(SCRIPT, run_name="__main__")
+        runpy.run_path(script, run_name="__main__")
     except SystemExit as exc:
         if exc.code not in (0, None):
             raise

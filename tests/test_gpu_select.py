@@ -141,3 +141,27 @@ def test_command_line_front_half(tmp_path, capsys):
     assert "Clusterize" in capsys.readouterr().out
     with pytest.raises(SystemExit):
         phyloselect.main(["-i", "x", "-m", "kmedoids", "-o", str(tmp_path), "-t"])
+
+
+def test_command_line_against_the_unmodified_reference_scripts(tmp_path):
+    """The matrices written by the reference's unmodified bin/phyloligo.py, clustered by its unmodified
+    bin/phyloselect.py (tests/golden/make_select_cli_golden.py): this command line on the same matrix files gives
+    the same data_cluster_indexes.dat and the same per-cluster FASTA files, byte for byte."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import make_cli_golden as mk
+    golden = dict(np.load(os.path.join(GOLDEN, "select_cli_golden.npz")))
+    fasta, n = mk.assembly()
+    path = os.path.join(tmp_path, "asm.fasta")
+    open(path, "wb").write(fasta)
+    assert len(golden["names"]) == 4
+    for name in golden["names"]:
+        mat = os.path.join(tmp_path, name + ".mat")
+        open(mat, "wb").write(golden[name + "_matrix_bytes"].tobytes())
+        out = os.path.join(tmp_path, name + "_sel")
+        assert phyloselect.main(["-i", mat, "-o", out, "-f", path] + str(golden[name + "_select_args"]).split()) == 0
+        assert open(os.path.join(out, "data_cluster_indexes.dat"), "rb").read() == golden[name + "_indexes"].tobytes(), name
+        files = sorted(f for f in os.listdir(out) if f.startswith("data_fasta_"))
+        assert files == [str(f) for f in golden[name + "_fasta_names"]], name
+        for f in files:
+            assert open(os.path.join(out, f), "rb").read() == golden[name + "_" + f].tobytes(), (name, f)
