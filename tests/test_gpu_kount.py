@@ -102,3 +102,27 @@ def test_worker_functions_and_command_line(tmp_path, capsys):
     for l, w in zip(lines, want):
         assert l[0] == w[0] and int(l[1]) == w[1] and int(l[2]) == w[2]
         assert float(l[3]) == pytest.approx(w[3], rel=1e-11, abs=1e-13)
+
+
+def test_command_line_against_the_unmodified_reference_script(tmp_path):
+    """Output files of the reference's unmodified bin/Kount.py (tests/golden/make_kount_cli_golden.py) against
+    this command line: same file names, same rows, ids and displayed coordinates identical, distances to 1e-11
+    (float64 logs and summation order differ from numpy's in the last bits)."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_kount_cli_golden as mk
+    golden = dict(np.load(os.path.join(HERE, "golden", "kount_cli_golden.npz")))
+    path = os.path.join(tmp_path, "asm.fasta")
+    open(path, "wb").write(mk.assembly())
+    assert len(golden["names"]) == 3
+    for name in golden["names"]:
+        outdir = os.path.join(tmp_path, str(name))
+        kount.main(["-i", path, "-u", "2", "-W", outdir] + str(golden[str(name) + "_args"]).split())
+        files = sorted(os.listdir(outdir))
+        assert files == [str(f) for f in golden[str(name) + "_files"]], name
+        for f in files:
+            want = [l.split("\t") for l in golden[str(name) + "_" + f].tobytes().decode().splitlines()]
+            got = [l.split("\t") for l in open(os.path.join(outdir, f)).read().splitlines()]
+            assert [r[:3] for r in got] == [r[:3] for r in want], (name, f)
+            g, w = np.array([float(r[3]) for r in got]), np.array([float(r[3]) for r in want])
+            assert np.allclose(g, w, rtol=1e-11, atol=1e-13), (name, f, np.abs(g - w).max())
