@@ -17,8 +17,14 @@
 //   * the row norms are float64 sums over the very same hi + lo values, and the epilogue
 //     evaluates n_a + n_b - 2 dot in float64.
 //   * entries whose Gram form cancels by more than 2^8 (n_a + n_b > 256 d^2: near-duplicate
-//     profiles) are recomputed exactly as sum (a-b)^2 by the warp that owns them, from a
-//     float32 copy of the profiles kept next to the operand blocks.
+//     profiles; 2^4 with the e4m3 cross terms below) are recomputed exactly as sum (a-b)^2 by the
+//     warp that owns them, from a float32 copy of the profiles kept next to the operand blocks.
+//   * cross terms in e4m3 (default; PO_EUCL_CROSS=f16 keeps them in float16): hi.lo + lo.hi is 2^-11
+//     of the dot product, so three mantissa bits are enough for it -- both factors are stored a
+//     second time as e4m3 (power-of-two scales from the largest |x'| of the matrix) and the two cross
+//     MMAs run as kind::f8f6f4 with K = 32, i.e. at half the cost of their float16 form: 2 MMA units per
+//     16 dimensions instead of 3.  Error against float64: ~2e-6 relative for ordinary pairs (float16
+//     cross terms: ~2e-8), below 4e-5 at the recomputation threshold; the stated tolerance is 1e-4.
 // Measured error against a float64 evaluation is ~1e-8 relative for ordinary pairs and below
 // 5e-5 at the cancellation threshold; the stated tolerance of this path is 1e-4
 // (BASELINE.json north_star).  PO_EUCL_EXACT=1 (or dim < 256) selects
@@ -34,6 +40,7 @@
 // the last commit all warps read the accumulators with tcgen05.ld, finish the distances and
 // store the tile (and its mirror) with coalesced stores.
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdlib.h>
 #include "po_common.cuh"
 #include "po_rank.cuh"
@@ -61,7 +68,12 @@ constexpr int GSUM_SLICES = 256;  // row slices of the two-stage (order-fixed, r
 int64_t gram_prepared_bytes(int64_t n, int64_t dim) {
     const int64_t npad = (n + GT - 1) / GT * GT;
     const int64_t ldk = gram_ldk(dim);
-    return npad * ldk * 4 + ldk * 8 + n * ldk * 4 + (int64_t)GSUM_SLICES * ldk * 8;
+    return npad * ldk * 4 + ldk * 8 + n * ldk * 4 + (int64_t)GSUM_SLICES * ldk * 8 + 64;  // + absmax / e4m3 scales
+}
+// e4m3 cross terms (default) or float16 cross terms (PO_EUCL_CROSS=f16): read at prepare AND at launch
+static bool eucl_cross8() {
+    const char* e = getenv("PO_EUCL_CROSS");
+    return !(e && e[0] == 'f' && e[1] == '1' && e[2] == '6');
 }
 
 // Spearman on the same kernel.  1 - rho is a Gram form as well: with r' = 2 rank - (dim + 1) (integer,
@@ -109,12 +121,44 @@ __global__ void __launch_bounds__(256) gram_colsum_final_kernel(const double* __
     sums[col] = s;
 }
 
-// One CTA per group of 128 profiles; the K blocks are walked in order so that a row's squared
-// norm is accumulated in a fixed order (reproducible, no atomics).
+// largest |x - mean| * 2^14 of the matrix (a maximum: order independent, reproducible)
 template <typename T>
+__global__ void __launch_bounds__(256) gram_absmax_kernel(const T* __restrict__ X, int64_t n, int64_t dim, int64_t ldx,
+                                                          const double* __restrict__ sums, unsigned* __restrict__ absmax_bits) {
+    const double inv_n = 1.0 / (double)n;
+    float m = 0.f;
+    const int64_t total = n * dim;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+        const int64_t r = e / dim, k = e - r * dim;
+        m = fmaxf(m, fabsf(((float)X[r * ldx + k] - (float)(sums[k] * inv_n)) * GSCALE));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(absmax_bits, __float_as_uint(m));
+}
+// scales[1] = alpha (hi -> e4m3: the largest value lands in [128, 256)), [2] = beta = 2^11 alpha (lo), [3] = 1 / (alpha beta)
+__global__ void gram_scales_kernel(float* scales) {
+    const float amax = __uint_as_float(reinterpret_cast<const unsigned*>(scales)[0]);
+    int e = 0;
+    float alpha = 1.f;
+    if (amax > 0.f && amax < 3.0e38f) {
+        frexpf(amax, &e);  // amax = m 2^e, m in [0.5, 1)
+        alpha = ldexpf(1.f, 8 - e);
+    }
+    scales[1] = alpha;
+    scales[2] = alpha * 2048.f;
+    scales[3] = 1.f / (alpha * alpha * 2048.f);
+}
+
+// One CTA per group of 128 profiles; the K blocks are walked in order so that a row's squared
+// norm is accumulated in a fixed order (reproducible, no atomics).  CROSS8: per 64-dimension block the
+// float16 hi plane (16 KB), then hi and lo as e4m3 (8 KB each; core matrices of 8 rows x 16 elements).
+template <typename T, bool CROSS8>
 __global__ void __launch_bounds__(256) gram_blocks_kernel(const T* __restrict__ X, int64_t n, int64_t dim, int64_t ldx,
                                                           const double* __restrict__ sums, unsigned char* __restrict__ P,
-                                                          int nkb, double* __restrict__ aux, float* __restrict__ X32) {
+                                                          int nkb, double* __restrict__ aux, float* __restrict__ X32,
+                                                          const float* __restrict__ scales) {
+    const float alpha = CROSS8 ? scales[1] : 1.f, beta = CROSS8 ? scales[2] : 1.f;
     const int64_t grp = blockIdx.x;
     const double inv_n = 1.0 / (double)n;
     double nrm[4] = {0.0, 0.0, 0.0, 0.0};
@@ -144,7 +188,20 @@ __global__ void __launch_bounds__(256) gram_blocks_kernel(const T* __restrict__ 
             }
             const size_t off = ((size_t)chunk * 16 + (row >> 3)) * 128 + (row & 7) * 16;
             *reinterpret_cast<uint4*>(blk_hi + off) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(blk_lo + off) = *reinterpret_cast<const uint4*>(lo);
+            if (!CROSS8) {
+                *reinterpret_cast<uint4*>(blk_lo + off) = *reinterpret_cast<const uint4*>(lo);
+            } else {
+                unsigned char h8[8], l8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    h8[e] = (unsigned char)__nv_cvt_float_to_fp8(__half2float(hi[e]) * alpha, __NV_SATFINITE, __NV_E4M3);
+                    l8[e] = (unsigned char)__nv_cvt_float_to_fp8(__half2float(lo[e]) * beta, __NV_SATFINITE, __NV_E4M3);
+                }
+                // 16-element core-matrix rows: two of this thread's 8-dimension chunks per row
+                const size_t off8 = ((size_t)(chunk >> 1) * 16 + (row >> 3)) * 128 + (row & 7) * 16 + (chunk & 1) * 8;
+                *reinterpret_cast<uint2*>(blk_lo + off8) = *reinterpret_cast<const uint2*>(h8);                   // hi as e4m3
+                *reinterpret_cast<uint2*>(blk_lo + GBLOCK_BYTES / 2 + off8) = *reinterpret_cast<const uint2*>(l8);  // lo as e4m3
+            }
         }
     }
 #pragma unroll
@@ -177,8 +234,18 @@ static int launch_gram_prepare_t(const void* d_X, int64_t n, int64_t dim, int64_
     gram_colsum_final_kernel<<<(unsigned)((ldk + 255) / 256), 256, 0, stream>>>(partial, dim, ldk, sums);
     count_launch(2);
     PO_LAUNCH_CHECK("gram_colsum_final_kernel");
-    gram_blocks_kernel<T><<<(unsigned)(npad / GT), 256, 0, stream>>>(reinterpret_cast<const T*>(d_X), n, dim, ldx, sums, P,
-                                                                    nkb, d_aux, X32);
+    float* scales = reinterpret_cast<float*>(P + npad * ldk * 4 + ldk * 8 + n * ldk * 4 + (int64_t)GSUM_SLICES * ldk * 8);
+    if (eucl_cross8()) {
+        PO_CUDA_CHECK(cudaMemsetAsync(scales, 0, 64, stream));
+        gram_absmax_kernel<T><<<1184, 256, 0, stream>>>(reinterpret_cast<const T*>(d_X), n, dim, ldx, sums,
+                                                        reinterpret_cast<unsigned*>(scales));
+        gram_scales_kernel<<<1, 1, 0, stream>>>(scales);
+        gram_blocks_kernel<T, true><<<(unsigned)(npad / GT), 256, 0, stream>>>(reinterpret_cast<const T*>(d_X), n, dim, ldx, sums,
+                                                                             P, nkb, d_aux, X32, scales);
+    } else {
+        gram_blocks_kernel<T, false><<<(unsigned)(npad / GT), 256, 0, stream>>>(reinterpret_cast<const T*>(d_X), n, dim, ldx, sums,
+                                                                              P, nkb, d_aux, X32, scales);
+    }
     count_launch(2);
     PO_LAUNCH_CHECK("gram_blocks_kernel");
     return PO_OK;
@@ -297,6 +364,15 @@ __device__ __forceinline__ void g_mma_f16(unsigned tmem_d, uint64_t adesc, uint6
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void g_mma_f8(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void g_mma_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -310,12 +386,13 @@ __device__ __forceinline__ void g_tmem_ld16(unsigned taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void g_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-enum GramMode { GM_EUCL = 0, GM_SC = 1 };
+enum GramMode { GM_EUCL = 0, GM_SC = 1, GM_EUCL8 = 2 };  // GM_EUCL8: Eucl with the cross terms as e4m3 MMAs
 
 struct GramParams {
     const unsigned char* P;  // operand blocks [n/128 groups][nkb][hi | lo][16 KB]
     const float* X32;        // float32 copy of the profiles, row pitch nkb * 64
     const double* aux;       // squared norms of the scaled, centred rows
+    const float* scales;     // GM_EUCL8: [3] = 1 / (alpha beta), the scale of the e4m3 cross accumulator
     int nkb;
     int64_t n;
     int64_t row0, row1, col0, col1;
@@ -350,6 +427,7 @@ template <> struct GramCfg<GM_EUCL> {
     static constexpr int NB = 1, KS = GRAM_EUCL_KS, STAGES = GRAM_EUCL_STAGES, GROUP_COLS = 256, TMEM_COLS = 256;
     static constexpr int THREADS = 256, CTAS = 2;
 };
+template <> struct GramCfg<GM_EUCL8> : GramCfg<GM_EUCL> {};
 template <> struct GramCfg<GM_SC> {
     static constexpr int NB = 1, KS = 64, STAGES = 3, GROUP_COLS = 384, TMEM_COLS = 512;
     static constexpr int THREADS = 512, CTAS = 1;
@@ -383,6 +461,8 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, unsigned tmem
     const double na = (INTERIOR || grow < p.n) ? p.aux[grow] : 0.0;
     const bool do_mirror = DIAG || ((p.flags & PO_FLAG_MIRROR) && row_base + GT <= col_base);
     const int64_t ldx32 = (int64_t)p.nkb * GK;
+    const float cross_scale = (MODE == GM_EUCL8) ? p.scales[3] : 1.f;
+    const double cancel_limit = (MODE == GM_EUCL8) ? 16.0 : 256.0;
     OUT_T* tbuf = reinterpret_cast<OUT_T*>(gsmem) + (size_t)warp * (32 * 33) + (size_t)lane * 33;
     const OUT_T* wb = reinterpret_cast<const OUT_T*>(gsmem) + (size_t)warp * (32 * 33);
     // where the transposed entries go: the mirror buffer, or (diagonal group) the group itself.
@@ -422,21 +502,21 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, unsigned tmem
                     val[j] = (OUT_T)v;
                     continue;
                 }
-                const float dot = __uint_as_float(vh[j]) + __uint_as_float(vx[j]);
+                const float dot = fmaf(__uint_as_float(vx[j]), cross_scale, __uint_as_float(vh[j]));
                 const double nsum = na + nb;
                 double d2 = nsum - 2.0 * (double)dot;
                 const bool on_diag = DIAG && r == c0 + j;
                 // a diagonal group recomputes for its entries right of the diagonal: the others are copies
                 const bool inside = DIAG ? (c0 + j > r && grow < p.n && col_base + c0 + j < p.n)
                                          : (INTERIOR || (row_ok && col_base + c0 + j >= p.col0 && col_base + c0 + j < p.col1));
-                if (inside && d2 * 256.0 < nsum) cancel |= 1u << j;
+                if (inside && d2 * cancel_limit < nsum) cancel |= 1u << j;
                 d2 = (d2 > 0.0 ? d2 : 0.0) * GUNSCALE;
                 if (sizeof(OUT_T) == 8) val[j] = (OUT_T)sqrt(d2);
                 else val[j] = (OUT_T)sqrtf((float)d2);
                 if (on_diag) val[j] = (OUT_T)0;  // sklearn forces an exact zero diagonal
             }
             // exact recomputation, one entry at a time, by the whole warp
-            unsigned lanes = (MODE == GM_EUCL) ? __ballot_sync(0xFFFFFFFFu, cancel != 0u) : 0u;
+            unsigned lanes = (MODE != GM_SC) ? __ballot_sync(0xFFFFFFFFu, cancel != 0u) : 0u;
             while (lanes) {
                 const int l = __ffs(lanes) - 1;
                 lanes &= lanes - 1;
@@ -574,6 +654,20 @@ __global__ void __launch_bounds__(GramCfg<MODE>::THREADS, GramCfg<MODE>::CTAS) g
             g_mbar_wait(empty0 + 8 * s, (unsigned)(((kq / NSTAGE) & 1) ^ 1));
             const unsigned dst = smem0 + s * STAGE_BYTES;
             g_mbar_expect_tx(full0 + 8 * s, stage_bytes);
+            if (MODE == GM_EUCL8) {
+                // per operand: the float16 hi plane of the stage (8 KB), then hi and lo as e4m3 (4 KB each);
+                // in memory a 64-dimension block is [hi f16 16 KB | hi e4m3 8 KB | lo e4m3 8 KB]
+                const int kb = (kq * KS) / GK, half = ((kq * KS) % GK) / KS;  // KS = 32: two stages per block
+                for (int o = 0; o < 2; ++o) {
+                    const unsigned char* blk = p.P + ((size_t)(o ? grp_b0 : grp_a) * nkb + kb) * 2 * GBLOCK_BYTES;
+                    const unsigned d0 = dst + o * 2 * SUB_BYTES;
+                    g_bulk_g2s(d0, blk + (size_t)half * SUB_BYTES, SUB_BYTES, full0 + 8 * s);
+                    g_bulk_g2s(d0 + SUB_BYTES, blk + GBLOCK_BYTES + (size_t)half * (SUB_BYTES / 2), SUB_BYTES / 2, full0 + 8 * s);
+                    g_bulk_g2s(d0 + SUB_BYTES + SUB_BYTES / 2, blk + GBLOCK_BYTES + GBLOCK_BYTES / 2 + (size_t)half * (SUB_BYTES / 2),
+                               SUB_BYTES / 2, full0 + 8 * s);
+                }
+                continue;
+            }
             g_bulk_g2s(dst, g_operand(grp_a, kq, 0), SUB_BYTES, full0 + 8 * s);
             g_bulk_g2s(dst + SUB_BYTES, g_operand(grp_a, kq, 1), SUB_BYTES, full0 + 8 * s);
 #pragma unroll
@@ -592,6 +686,23 @@ __global__ void __launch_bounds__(GramCfg<MODE>::THREADS, GramCfg<MODE>::CTAS) g
             g_mbar_wait(full0 + 8 * s, (unsigned)((kq / NSTAGE) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const unsigned a_hi = smem0 + s * STAGE_BYTES, a_lo = a_hi + SUB_BYTES;
+            if (MODE == GM_EUCL8) {
+                // stage: A [hi f16 8 KB | hi e4m3 4 KB | lo e4m3 4 KB], then B the same.  Two float16 MMAs (K = 16
+                // each) for hi.hi and two e4m3 MMAs (K = 32 each) for the cross terms, interleaved so that no
+                // accumulator receives two MMAs back to back; a tile below the diagonal issues the cross terms
+                // in the order its mirror image does (bitwise symmetry).
+                const unsigned b_hi = a_hi + 2 * SUB_BYTES;
+                const unsigned a_h8 = a_hi + SUB_BYTES, a_l8 = a_h8 + SUB_BYTES / 2;
+                const unsigned b_h8 = b_hi + SUB_BYTES, b_l8 = b_h8 + SUB_BYTES / 2;
+                const bool upper = col_base >= row_base;
+                const unsigned acc = kq > 0 ? 1u : 0u;
+                g_mma_f8(tmem + GT, g_smem_desc(upper ? a_h8 : a_l8), g_smem_desc(upper ? b_l8 : b_h8), idesc, acc);
+                g_mma_f16(tmem, g_smem_desc(a_hi), g_smem_desc(b_hi), idesc, acc);
+                g_mma_f8(tmem + GT, g_smem_desc(upper ? a_l8 : a_h8), g_smem_desc(upper ? b_h8 : b_l8), idesc, 1u);
+                g_mma_f16(tmem, g_smem_desc(a_hi + 2 * 2048), g_smem_desc(b_hi + 2 * 2048), idesc, 1u);
+                g_mma_commit(empty0 + 8 * s);
+                continue;
+            }
 #pragma unroll
             for (int ks = 0; ks < KS / 16; ++ks) {
                 const unsigned koff = ks * 2 * 2048;  // two 8-element chunks per MMA
@@ -653,7 +764,7 @@ __global__ void __launch_bounds__(GramCfg<MODE>::THREADS, GramCfg<MODE>::CTAS) g
         const unsigned tg = tmem + (unsigned)(g * Cfg::GROUP_COLS);
         // groups wholly inside the requested block (all but the ragged edges) skip the per-entry bounds tests
         const bool interior = row_base >= p.row0 && row_base + GT <= p.row1 && cb >= p.col0 && cb + GT <= p.col1;
-        if (MODE == GM_EUCL && cb == row_base)
+        if (MODE != GM_SC && cb == row_base)
             gram_epilogue<OUT_T, MODE, false, true>(p, tg, row_base, cb, s_nb + g * GT, gsmem);
         else if (interior)
             gram_epilogue<OUT_T, MODE, true, false>(p, tg, row_base, cb, s_nb + g * GT, gsmem);
@@ -698,6 +809,7 @@ int launch_gram(int metric, const void* d_P, const double* d_aux, int64_t n, int
     {
         const int64_t ldk = gram_ldk(dim), npad = (n + GT - 1) / GT * GT;
         p.X32 = reinterpret_cast<const float*>(p.P + npad * ldk * 4 + ldk * 8);
+        p.scales = reinterpret_cast<const float*>(p.P + npad * ldk * 4 + ldk * 8 + n * ldk * 4 + (int64_t)GSUM_SLICES * ldk * 8);
     }
     p.n = n;
     p.row0 = row0; p.row1 = row1; p.col0 = col0; p.col1 = col1;
@@ -710,6 +822,9 @@ int launch_gram(int metric, const void* d_P, const double* d_aux, int64_t n, int
     if (metric == PO_SC)
         rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_SC>(p, row1, col1, stream)
                                  : launch_gram_t<double, GM_SC>(p, row1, col1, stream);
+    else if (eucl_cross8())
+        rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_EUCL8>(p, row1, col1, stream)
+                                 : launch_gram_t<double, GM_EUCL8>(p, row1, col1, stream);
     else
         rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_EUCL>(p, row1, col1, stream)
                                  : launch_gram_t<double, GM_EUCL>(p, row1, col1, stream);
