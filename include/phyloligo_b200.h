@@ -125,9 +125,10 @@ int po_profile_batch(const uint8_t* d_text, const int64_t* d_begin, const int64_
  *               cross terms -- or float16 hi and lo with PO_EUCL_CROSS=f16), float64 column sums, a
  *               float32 copy of the profiles for the exact recomputation of cancelling entries, and
  *               the e4m3 scales
- *   SC        : 64 <= dim <= 4096: the centred doubled average ranks 2 rank - (dim+1) as two float16
- *               integer digits (r = 64 hi + lo) in the EuclGram block layout (n rounded up to 128,
- *               dim to 64, 4 bytes per element) -- Spearman runs on the tensor cores, exactly;
+ *   SC        : 64 <= dim <= 4096: the centred doubled average ranks 2 rank - (dim+1) as two int8
+ *               digits (r = 128 h + l; PO_SC_DIGITS=f16: two float16 digits, r = 64 h + l) in the
+ *               tensor-core block layout (n rounded up to 128, dim to 64; the buffer is sized for the
+ *               float16 form, 4 bytes per element) -- Spearman runs on the tensor cores, exactly;
  *               otherwise n rows of dim (rounded up to 4) int32 ranks for the CUDA-core kernel
  *   KT        : n rows of packed order-relation bit masks, 2 * ceil(dim(dim-1)/2 / 128) * 16 bytes
  *   JSD       : float32 with exact zeros biased to 1e-30, dim rounded up to a multiple of 32

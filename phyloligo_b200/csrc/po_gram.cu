@@ -90,9 +90,16 @@ bool sc_use_gram(int metric, int64_t dim) {
     if (e && e[0] == '1') return false;
     return dim >= 64 && dim <= 4096;
 }
+// Digits as int8 for kind::i8 MMAs (default: r' = 128 h + l, l in [-64, 63], |h| <= 32; int32 accumulators,
+// exact by construction, K = 32 per MMA: half the tensor time of the float16 digits) or as float16
+// (PO_SC_DIGITS=f16: r' = 64 h + l).  Read at prepare AND at launch.
+static bool sc_digits8() {
+    const char* e = getenv("PO_SC_DIGITS");
+    return !(e && e[0] == 'f' && e[1] == '1' && e[2] == '6');
+}
 int64_t sc_gram_prepared_bytes(int64_t n, int64_t dim) {
     const int64_t npad = (n + GT - 1) / GT * GT;
-    return npad * gram_ldk(dim) * 4;
+    return npad * gram_ldk(dim) * 4;  // the int8 digits use the first half
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,7 +271,7 @@ int launch_gram_prepare(const void* d_X, int dtype, int64_t n, int64_t dim, int6
 // SC operands: one CTA per profile ranks it (O(dim^2) comparisons out of shared memory, as
 // prepare_rank_kernel of po_prepare.cu) and scatters the two float16 digits of every centred doubled
 // rank into the hi / lo operand blocks.  The block region is zeroed first (padding rows and dimensions).
-template <typename T>
+template <typename T, bool DIGITS8>
 __global__ void __launch_bounds__(256) sc_blocks_kernel(const T* __restrict__ X, int64_t n, int64_t dim, int64_t ldx,
                                                         unsigned char* __restrict__ P, int nkb, int dpad,
                                                         double* __restrict__ aux) {
@@ -275,6 +282,17 @@ __global__ void __launch_bounds__(256) sc_blocks_kernel(const T* __restrict__ X,
     const int64_t grp = row / GT;
     const int rr = (int)(row % GT);
     unsigned long long ss = rank_transform_row<T>(X + row * ldx, (int)dim, dpad, g_rank_smem, [&](int e, int val) {
+        if (DIGITS8) {
+            // a 64-dimension block is [h int8 8 KB | l int8 8 KB]; core matrices of 8 rows x 16 elements
+            const int lo = ((val + 64) & 127) - 64;  // [-64, 63]
+            const int hi = (val - lo) / 128;         // exact, |hi| <= 32
+            const int kb = e / GK, kk = e % GK;
+            unsigned char* blk = P + ((size_t)grp * nkb + kb) * GBLOCK_BYTES;
+            const size_t off = ((size_t)(kk >> 4) * 16 + (rr >> 3)) * 128 + (rr & 7) * 16 + (kk & 15);
+            blk[off] = (unsigned char)(signed char)hi;
+            blk[GBLOCK_BYTES / 2 + off] = (unsigned char)(signed char)lo;
+            return;
+        }
         const int lo = ((val + 32) & 63) - 32;     // [-32, 31]
         const int hi = (val - lo) / 64;            // exact
         const int kb = e / GK, kk = e % GK;
@@ -300,15 +318,21 @@ int launch_sc_gram_prepare(const void* d_X, int dtype, int64_t n, int64_t dim, i
     PO_CUDA_CHECK(cudaMemsetAsync(d_P, 0, (size_t)sc_gram_prepared_bytes(n, dim), stream));
     const size_t sm = rank_smem_bytes(dim);
     const int dpad = (int)rank_pad(dim);
+#define PO_SC_PREP(TT, D8)                                                                                              \
+    do {                                                                                                                \
+        PO_CUDA_CHECK(cudaFuncSetAttribute(sc_blocks_kernel<TT, D8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        sc_blocks_kernel<TT, D8><<<(unsigned)n, 256, sm, stream>>>(reinterpret_cast<const TT*>(d_X), n, dim, ldx,         \
+                                                                   reinterpret_cast<unsigned char*>(d_P), nkb, dpad, d_aux); \
+    } while (0)
+    const bool d8 = sc_digits8();
     if (dtype == PO_F32) {
-        PO_CUDA_CHECK(cudaFuncSetAttribute(sc_blocks_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        sc_blocks_kernel<float><<<(unsigned)n, 256, sm, stream>>>(reinterpret_cast<const float*>(d_X), n, dim, ldx,
-                                                                  reinterpret_cast<unsigned char*>(d_P), nkb, dpad, d_aux);
+        if (d8) PO_SC_PREP(float, true);
+        else PO_SC_PREP(float, false);
     } else {
-        PO_CUDA_CHECK(cudaFuncSetAttribute(sc_blocks_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        sc_blocks_kernel<double><<<(unsigned)n, 256, sm, stream>>>(reinterpret_cast<const double*>(d_X), n, dim, ldx,
-                                                                   reinterpret_cast<unsigned char*>(d_P), nkb, dpad, d_aux);
+        if (d8) PO_SC_PREP(double, true);
+        else PO_SC_PREP(double, false);
     }
+#undef PO_SC_PREP
     count_launch(2);
     PO_LAUNCH_CHECK("sc_blocks_kernel");
     return PO_OK;
@@ -373,6 +397,15 @@ __device__ __forceinline__ void g_mma_f8(unsigned tmem_d, uint64_t adesc, uint64
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void g_mma_i8(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void g_mma_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -386,7 +419,8 @@ __device__ __forceinline__ void g_tmem_ld16(unsigned taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void g_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-enum GramMode { GM_EUCL = 0, GM_SC = 1, GM_EUCL8 = 2 };  // GM_EUCL8: Eucl with the cross terms as e4m3 MMAs
+enum GramMode { GM_EUCL = 0, GM_SC = 1, GM_EUCL8 = 2, GM_SC8 = 3 };  // GM_EUCL8: e4m3 cross terms; GM_SC8: int8 digits
+__host__ __device__ constexpr bool gm_is_sc(int mode) { return mode == GM_SC || mode == GM_SC8; }
 
 struct GramParams {
     const unsigned char* P;  // operand blocks [n/128 groups][nkb][hi | lo][16 KB]
@@ -425,12 +459,16 @@ template <int MODE> struct GramCfg;
 #endif
 template <> struct GramCfg<GM_EUCL> {
     static constexpr int NB = 1, KS = GRAM_EUCL_KS, STAGES = GRAM_EUCL_STAGES, GROUP_COLS = 256, TMEM_COLS = 256;
-    static constexpr int THREADS = 256, CTAS = 2;
+    static constexpr int THREADS = 256, CTAS = 2, ELEM_BYTES = 2;
 };
 template <> struct GramCfg<GM_EUCL8> : GramCfg<GM_EUCL> {};
+template <> struct GramCfg<GM_SC8> {  // 128-wide stages of int8 digits: A [h 16 KB | l 16 KB], B the same: 64 KB
+    static constexpr int NB = 1, KS = 128, STAGES = 3, GROUP_COLS = 384, TMEM_COLS = 512;
+    static constexpr int THREADS = 512, CTAS = 1, ELEM_BYTES = 1;
+};
 template <> struct GramCfg<GM_SC> {
     static constexpr int NB = 1, KS = 64, STAGES = 3, GROUP_COLS = 384, TMEM_COLS = 512;
-    static constexpr int THREADS = 512, CTAS = 1;
+    static constexpr int THREADS = 512, CTAS = 1, ELEM_BYTES = 2;
 };
 
 // Epilogue of one 128 x 128 group of a tile, by all warps of the CTA.  Warp w owns TMEM lanes
@@ -481,21 +519,21 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, unsigned tmem
             const unsigned ta = tmem + ((unsigned)(lq * 32) << 16) + (unsigned)c0;
             g_tmem_ld16(ta, vh);
             g_tmem_ld16(ta + GT, vx);
-            if (MODE == GM_SC) {
-                g_tmem_ld16(ta + 2 * GT, vy);
-                g_tmem_ld16(ta + 3 * GT, vz);
-            }
+            if (gm_is_sc(MODE)) g_tmem_ld16(ta + 2 * GT, vy);
+            if (MODE == GM_SC) g_tmem_ld16(ta + 3 * GT, vz);
             g_tmem_wait_ld();
             OUT_T val[16];
             unsigned cancel = 0u;  // columns of this chunk whose Gram form cancelled too much
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const double nb = s_nb[c0 + j];
-                if (MODE == GM_SC) {
+                if (gm_is_sc(MODE)) {
                     // exact integer dot product of the centred doubled ranks, then 1 - rho as K_SC does
-                    const long long t = 4096ll * (long long)__uint_as_float(vh[j]) +
-                                        64ll * ((long long)__uint_as_float(vx[j]) + (long long)__uint_as_float(vy[j])) +
-                                        (long long)__uint_as_float(vz[j]);
+                    const long long t = (MODE == GM_SC8)
+                        ? 16384ll * (long long)(int)vh[j] + 128ll * (long long)(int)vx[j] + (long long)(int)vy[j]  // hh, hl + lh, ll (int32)
+                        : 4096ll * (long long)__uint_as_float(vh[j]) +
+                              64ll * ((long long)__uint_as_float(vx[j]) + (long long)__uint_as_float(vy[j])) +
+                              (long long)__uint_as_float(vz[j]);
                     const double den = sqrt(na * nb);
                     const double v = (den == 0.0) ? __longlong_as_double(0x7FF8000000000000ll)  // scipy: NaN for a constant row
                                                   : 1.0 - (double)t / den;
@@ -516,7 +554,7 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, unsigned tmem
                 if (on_diag) val[j] = (OUT_T)0;  // sklearn forces an exact zero diagonal
             }
             // exact recomputation, one entry at a time, by the whole warp
-            unsigned lanes = (MODE != GM_SC) ? __ballot_sync(0xFFFFFFFFu, cancel != 0u) : 0u;
+            unsigned lanes = !gm_is_sc(MODE) ? __ballot_sync(0xFFFFFFFFu, cancel != 0u) : 0u;
             while (lanes) {
                 const int l = __ffs(lanes) - 1;
                 lanes &= lanes - 1;
@@ -584,7 +622,7 @@ template <typename OUT_T, int MODE>
 __global__ void __launch_bounds__(GramCfg<MODE>::THREADS, GramCfg<MODE>::CTAS) gram_tile_kernel(const GramParams p) {
     using Cfg = GramCfg<MODE>;
     constexpr int NB = Cfg::NB, KS = Cfg::KS, NSTAGE = Cfg::STAGES;
-    constexpr int SUB_BYTES = GT * KS * 2;               // one operand (hi or lo) of one 128-profile group per stage
+    constexpr int SUB_BYTES = GT * KS * Cfg::ELEM_BYTES;  // one operand (hi or lo) of one 128-profile group per stage
     constexpr int STAGE_BYTES = (1 + NB) * 2 * SUB_BYTES;  // A hi, A lo, then B hi, B lo per group
     constexpr int TILE_N = NB * GT;
     extern __shared__ __align__(1024) unsigned char gsmem[];
@@ -635,7 +673,7 @@ __global__ void __launch_bounds__(GramCfg<MODE>::THREADS, GramCfg<MODE>::CTAS) g
     const unsigned tmem = s_tmem;
 
     const int nkb = p.nkb;
-    const int nks = nkb * (GK / KS);  // K stages of the tile
+    const int nks = (nkb * GK + KS - 1) / KS;  // K stages of the tile
     // operand (grp, stage kq, hi/lo): the KS-wide slice of the 64-wide block, chunk-major inside the block
     auto g_operand = [&](int64_t grp, int kq, int hl) -> const unsigned char* {
         const int kb = (kq * KS) / GK;
@@ -653,6 +691,21 @@ __global__ void __launch_bounds__(GramCfg<MODE>::THREADS, GramCfg<MODE>::CTAS) g
             const int s = kq % NSTAGE;
             g_mbar_wait(empty0 + 8 * s, (unsigned)(((kq / NSTAGE) & 1) ^ 1));
             const unsigned dst = smem0 + s * STAGE_BYTES;
+            if (MODE == GM_SC8) {
+                // a 128-dimension stage = two 64-dimension blocks [h int8 8 KB | l int8 8 KB]; per operand the two
+                // h planes go next to each other (8 chunks of 16 dimensions, 2 KB apart), then the two l planes
+                const int nblk = min(2, nkb - 2 * kq);
+                g_mbar_expect_tx(full0 + 8 * s, (unsigned)(nblk * 2 * GBLOCK_BYTES));
+                for (int o = 0; o < 2; ++o) {
+                    const unsigned d0 = dst + o * 2 * SUB_BYTES;
+                    for (int b = 0; b < nblk; ++b) {
+                        const unsigned char* blk = p.P + ((size_t)(o ? grp_b0 : grp_a) * nkb + 2 * kq + b) * GBLOCK_BYTES;
+                        g_bulk_g2s(d0 + b * (GBLOCK_BYTES / 2), blk, GBLOCK_BYTES / 2, full0 + 8 * s);
+                        g_bulk_g2s(d0 + SUB_BYTES + b * (GBLOCK_BYTES / 2), blk + GBLOCK_BYTES / 2, GBLOCK_BYTES / 2, full0 + 8 * s);
+                    }
+                }
+                continue;
+            }
             g_mbar_expect_tx(full0 + 8 * s, stage_bytes);
             if (MODE == GM_EUCL8) {
                 // per operand: the float16 hi plane of the stage (8 KB), then hi and lo as e4m3 (4 KB each);
@@ -686,6 +739,25 @@ __global__ void __launch_bounds__(GramCfg<MODE>::THREADS, GramCfg<MODE>::CTAS) g
             g_mbar_wait(full0 + 8 * s, (unsigned)((kq / NSTAGE) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const unsigned a_hi = smem0 + s * STAGE_BYTES, a_lo = a_hi + SUB_BYTES;
+            if (MODE == GM_SC8) {
+                // int8 digits, int32 accumulators: hh, hl + lh (one accumulator: integer sums do not care about
+                // the order) and ll; issue order hh, hl, ll, lh keeps the two cross MMAs apart
+                const unsigned idesc8 = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(GT >> 3) << 17) | ((unsigned)(GT >> 4) << 24);
+                const unsigned b_hi = a_hi + 2 * SUB_BYTES, b_lo = b_hi + SUB_BYTES;
+                const int steps = 2 * min(2, nkb - 2 * kq);  // K = 32 per MMA, 64 dimensions per block
+                for (int ks = 0; ks < steps; ++ks) {
+                    const unsigned koff = ks * 2 * 2048;  // two 16-element chunks per MMA
+                    const unsigned acc = (kq > 0 || ks > 0) ? 1u : 0u;
+                    const uint64_t dah = g_smem_desc(a_hi + koff), dal = g_smem_desc(a_lo + koff);
+                    const uint64_t dbh = g_smem_desc(b_hi + koff), dbl = g_smem_desc(b_lo + koff);
+                    g_mma_i8(tmem, dah, dbh, idesc8, acc);
+                    g_mma_i8(tmem + GT, dah, dbl, idesc8, acc);
+                    g_mma_i8(tmem + 2 * GT, dal, dbl, idesc8, acc);
+                    g_mma_i8(tmem + GT, dal, dbh, idesc8, 1u);
+                }
+                g_mma_commit(empty0 + 8 * s);
+                continue;
+            }
             if (MODE == GM_EUCL8) {
                 // stage: A [hi f16 8 KB | hi e4m3 4 KB | lo e4m3 4 KB], then B the same.  Two float16 MMAs (K = 16
                 // each) for hi.hi and two e4m3 MMAs (K = 32 each) for the cross terms, interleaved so that no
@@ -764,7 +836,7 @@ __global__ void __launch_bounds__(GramCfg<MODE>::THREADS, GramCfg<MODE>::CTAS) g
         const unsigned tg = tmem + (unsigned)(g * Cfg::GROUP_COLS);
         // groups wholly inside the requested block (all but the ragged edges) skip the per-entry bounds tests
         const bool interior = row_base >= p.row0 && row_base + GT <= p.row1 && cb >= p.col0 && cb + GT <= p.col1;
-        if (MODE != GM_SC && cb == row_base)
+        if (!gm_is_sc(MODE) && cb == row_base)
             gram_epilogue<OUT_T, MODE, false, true>(p, tg, row_base, cb, s_nb + g * GT, gsmem);
         else if (interior)
             gram_epilogue<OUT_T, MODE, true, false>(p, tg, row_base, cb, s_nb + g * GT, gsmem);
@@ -789,7 +861,7 @@ static int launch_gram_t(GramParams p, int64_t row1, int64_t col1, cudaStream_t 
     }
     p.tiles_r = tr;
     p.tiles_c = tc;
-    const size_t smem = (size_t)Cfg::STAGES * (1 + Cfg::NB) * 2 * GT * Cfg::KS * 2 + 1024;
+    const size_t smem = (size_t)Cfg::STAGES * (1 + Cfg::NB) * 2 * GT * Cfg::KS * Cfg::ELEM_BYTES + 1024;
     PO_CUDA_CHECK(cudaFuncSetAttribute(gram_tile_kernel<OUT_T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gram_tile_kernel<OUT_T, MODE><<<dim3((unsigned)(tr * tc), 1, 1), Cfg::THREADS, smem, stream>>>(p);
     return PO_OK;
@@ -819,7 +891,10 @@ int launch_gram(int metric, const void* d_P, const double* d_aux, int64_t n, int
     p.flags = flags;
     LaunchTimer tm(1, stream);
     int rc;
-    if (metric == PO_SC)
+    if (metric == PO_SC && sc_digits8())
+        rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_SC8>(p, row1, col1, stream)
+                                 : launch_gram_t<double, GM_SC8>(p, row1, col1, stream);
+    else if (metric == PO_SC)
         rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_SC>(p, row1, col1, stream)
                                  : launch_gram_t<double, GM_SC>(p, row1, col1, stream);
     else if (eucl_cross8())
