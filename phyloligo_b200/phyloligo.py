@@ -338,29 +338,26 @@ def compute_distances_device(frequencies, metric="Eucl"):
     if X.shape[0] < 2 * TILE * world:
         res = engine.distance_matrix_device(X, metric, torch.float64, symmetric=True).cpu().numpy()
         return res if rank == 0 else None
-    import torch.distributed as dist
-    from . import multigpu, sharding
+    # Every rank ships the rows it owns into one scratch file in shared memory (the same sink as the --large
+    # outputs: nothing the size of the matrix is ever allocated on a device or sent through rank 0's GPU) and
+    # rank 0 reads the matrix back as the in-RAM float64 array of this convention.
     n = int(X.shape[0])
-    P, aux, dim = engine.prepare(X, metric)
-    job = multigpu.BlockRows(n, torch.float64, rank, world)
-    job.compute(metric, P, aux, dim)
-    full = torch.empty((n, n), dtype=torch.float64, device=device) if rank == 0 else None
-    ops = []
-    for i, (a, b) in enumerate(job.ranges):
-        if b <= a:
-            continue
-        owner = sharding.range_owner(i, world)
-        if rank == 0 and owner == 0:
-            full[a:b].copy_(job.out_rows[i])
-        elif rank == 0:
-            ops.append(dist.P2POp(dist.irecv, full[a:b], owner))
-        elif owner == rank:
-            ops.append(dist.P2POp(dist.isend, job.out_rows[i], 0))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-    res = full.cpu().numpy() if rank == 0 else None
-    job.close()
+    scratch_dir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = None
+    if rank == 0:
+        fd, path = tempfile.mkstemp(prefix="phyloligo_b200_", suffix=".f64", dir=scratch_dir)
+        os.close(fd)
+    path = _broadcast_str(path)
+    fm = _open_file_matrix(path, n, dtype=np.float64)
+    try:
+        _fill_host_matrix(fm.array, X, metric)
+    finally:
+        fm.close()
+    _barrier()
+    res = None
+    if rank == 0:
+        res = np.fromfile(path, dtype=np.float64).reshape(n, n)
+        os.unlink(path)
     return res
 
 
@@ -376,7 +373,7 @@ def _my_row_ranges(n, rank, world):
     return [ranges[i] for i in sharding.owned_ranges(ranges, rank, world) if ranges[i][1] > ranges[i][0]]
 
 
-def _open_file_matrix(path, n, offset=0, create=True, fresh=None):
+def _open_file_matrix(path, n, offset=0, create=True, fresh=None, dtype=np.float32):
     """The output region as a hostsink.FileMatrix whose pages (of this rank's rows) are being instantiated.
     Rank 0 creates the file, the others attach after the barrier."""
     rank, world = ranks()
@@ -386,10 +383,10 @@ def _open_file_matrix(path, n, offset=0, create=True, fresh=None):
     if fm is not None:
         fm.close()
     if rank == 0:
-        fm = hostsink.FileMatrix(path, n, n, np.float32, offset, create=create)
+        fm = hostsink.FileMatrix(path, n, n, dtype, offset, create=create)
     _barrier()
     if rank != 0:
-        fm = hostsink.FileMatrix(path, n, n, np.float32, offset, create=False)
+        fm = hostsink.FileMatrix(path, n, n, dtype, offset, create=False)
     # rank 0 knows whether the file's pages exist already
     fresh = fresh if fresh is not None else _broadcast_str(fm.fresh if rank == 0 else None)
     threads = hostsink.host_threads(world)
