@@ -122,7 +122,7 @@ int po_profile_batch(const uint8_t* d_text, const int64_t* d_begin, const int64_
  *   Eucl / BC : n rows of dim rounded up to a multiple of 4, float32
  *   EuclGram  : centred operand blocks for the tensor-core kernel (n rounded up to 128, dim to 64,
  *               4 bytes per element: the float16 hi part, and hi and lo once more as e4m3 for the
- *               cross terms -- or float16 hi and lo with PO_EUCL_CROSS=f16), float64 column sums, a
+ *               cross terms -- or float16 hi and lo below 1024 dimensions / with PO_EUCL_CROSS=f16), float64 column sums, a
  *               float32 copy of the profiles for the exact recomputation of cancelling entries, and
  *               the e4m3 scales
  *   SC        : 64 <= dim <= 4096: the centred doubled average ranks 2 rank - (dim+1) as two int8
@@ -184,7 +184,7 @@ int po_rank_transform(const void* d_X, int dtype, int64_t n, int64_t dim, int64_
  *                caller's `out` addresses the full matrix (mirrored entries
  *                (c, r) must be addressable).
  * Values: Eucl = sqrt(sum (a-b)^2) (PO_EUCL_GRAM: Gram form on the tensor cores, exact 0 on the
- * diagonal, stated tolerance 1e-4 relative, measured <= 5e-6; PO_EUCL_CROSS=f16: <= 4e-7); JSD in nats (core/phylodist.py:22), 0 for
+ * diagonal, stated tolerance 1e-4 relative, measured <= 5e-6); JSD in nats (core/phylodist.py:22), 0 for
  * identical rows, ln(2)/2 against an all-zero row; BC = sum|a-b| / sum|a+b|;
  * KT = 1 - (1 - tau_b) (tau_b itself; 0 when a row is constant); SC = 1 - rho
  * (NaN when a row is constant).

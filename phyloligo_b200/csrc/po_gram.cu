@@ -17,9 +17,9 @@
 //   * the row norms are float64 sums over the very same hi + lo values, and the epilogue
 //     evaluates n_a + n_b - 2 dot in float64.
 //   * entries whose Gram form cancels by more than 2^8 (n_a + n_b > 256 d^2: near-duplicate
-//     profiles; 2^4 with the e4m3 cross terms below) are recomputed exactly as sum (a-b)^2 by the
+//     profiles; 2^3 with the e4m3 cross terms below) are recomputed exactly as sum (a-b)^2 by the
 //     warp that owns them, from a float32 copy of the profiles kept next to the operand blocks.
-//   * cross terms in e4m3 (default; PO_EUCL_CROSS=f16 keeps them in float16): hi.lo + lo.hi is 2^-11
+//   * cross terms in e4m3 (from 1024 dimensions up; PO_EUCL_CROSS=f16 keeps them in float16): hi.lo + lo.hi is 2^-11
 //     of the dot product, so three mantissa bits are enough for it -- both factors are stored a
 //     second time as e4m3 (power-of-two scales from the largest |x'| of the matrix) and the two cross
 //     MMAs run as kind::f8f6f4 with K = 32, i.e. at half the cost of their float16 form: 2 MMA units per
@@ -70,10 +70,15 @@ int64_t gram_prepared_bytes(int64_t n, int64_t dim) {
     const int64_t ldk = gram_ldk(dim);
     return npad * ldk * 4 + ldk * 8 + n * ldk * 4 + (int64_t)GSUM_SLICES * ldk * 8 + 64;  // + absmax / e4m3 scales
 }
-// e4m3 cross terms (default) or float16 cross terms (PO_EUCL_CROSS=f16): read at prepare AND at launch
-static bool eucl_cross8() {
+// e4m3 cross terms from 1024 dimensions up, float16 cross terms below (or everywhere with PO_EUCL_CROSS=f16);
+// read at prepare AND at launch.  The e4m3 rounding of the cross terms is bounded by ~3e-5 C relative on a
+// distance (C = cancellation factor, entries with C > 8 are recomputed exactly) and averages out over the
+// dimensions: measured 6.5e-7 at 4096 dimensions but 2e-5 on short-contig 256-dimension profiles, too close
+// to the stated 1e-4 -- and at 256 dimensions the kernel is bound by its epilogue, not by the MMAs.
+static bool eucl_cross8(int64_t dim) {
     const char* e = getenv("PO_EUCL_CROSS");
-    return !(e && e[0] == 'f' && e[1] == '1' && e[2] == '6');
+    if (e && e[0] == 'f' && e[1] == '1' && e[2] == '6') return false;
+    return dim >= 1024;
 }
 
 // Spearman on the same kernel.  1 - rho is a Gram form as well: with r' = 2 rank - (dim + 1) (integer,
@@ -242,7 +247,7 @@ static int launch_gram_prepare_t(const void* d_X, int64_t n, int64_t dim, int64_
     count_launch(2);
     PO_LAUNCH_CHECK("gram_colsum_final_kernel");
     float* scales = reinterpret_cast<float*>(P + npad * ldk * 4 + ldk * 8 + n * ldk * 4 + (int64_t)GSUM_SLICES * ldk * 8);
-    if (eucl_cross8()) {
+    if (eucl_cross8(dim)) {
         PO_CUDA_CHECK(cudaMemsetAsync(scales, 0, 64, stream));
         gram_absmax_kernel<T><<<1184, 256, 0, stream>>>(reinterpret_cast<const T*>(d_X), n, dim, ldx, sums,
                                                         reinterpret_cast<unsigned*>(scales));
@@ -500,7 +505,7 @@ __device__ __forceinline__ void gram_epilogue(const GramParams& p, unsigned tmem
     const bool do_mirror = DIAG || ((p.flags & PO_FLAG_MIRROR) && row_base + GT <= col_base);
     const int64_t ldx32 = (int64_t)p.nkb * GK;
     const float cross_scale = (MODE == GM_EUCL8) ? p.scales[3] : 1.f;
-    const double cancel_limit = (MODE == GM_EUCL8) ? 16.0 : 256.0;
+    const double cancel_limit = (MODE == GM_EUCL8) ? 8.0 : 256.0;
     OUT_T* tbuf = reinterpret_cast<OUT_T*>(gsmem) + (size_t)warp * (32 * 33) + (size_t)lane * 33;
     const OUT_T* wb = reinterpret_cast<const OUT_T*>(gsmem) + (size_t)warp * (32 * 33);
     // where the transposed entries go: the mirror buffer, or (diagonal group) the group itself.
@@ -897,7 +902,7 @@ int launch_gram(int metric, const void* d_P, const double* d_aux, int64_t n, int
     else if (metric == PO_SC)
         rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_SC>(p, row1, col1, stream)
                                  : launch_gram_t<double, GM_SC>(p, row1, col1, stream);
-    else if (eucl_cross8())
+    else if (eucl_cross8(dim))
         rc = out_dtype == PO_F32 ? launch_gram_t<float, GM_EUCL8>(p, row1, col1, stream)
                                  : launch_gram_t<double, GM_EUCL8>(p, row1, col1, stream);
     else
