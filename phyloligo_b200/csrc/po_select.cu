@@ -125,12 +125,22 @@ __global__ void cluster_finish_kernel(const unsigned long long* min_key, const l
 }
 
 // k nearest neighbours of every row, the row's own column excluded: ascending distance, ties by
-// column index.  One CTA per row.  A radix select over the order-preserving 32-bit keys of the row's
+// column index.  One CTA per row.
+// Fast path (one pass over the row, HBM bound): 8192 entries of the row -- 64 evenly spaced runs of 128
+// consecutive columns, or the whole row when it is that short -- are loaded into shared memory and a radix
+// select over them gives a threshold at about twice the sample rank that corresponds to k; one pass over
+// the row then gathers every entry at or below the threshold (k of them are guaranteed to be the k
+// smallest; about 2k + 200 are expected), which are sorted by (distance, column).  When fewer than k or
+// more than 4096 entries pass (an unlucky sample, massive ties, NaN rows) the row falls back to the
+// exact path.
+// Exact path (five passes): a radix select over the order-preserving 32-bit keys of the row's
 // entries (four 8-bit passes, each a shared-memory histogram of the still undecided prefix class) finds
 // the key of the k-th smallest entry; everything strictly below it, then the first ties in column
 // order, are gathered and sorted in shared memory (bitonic, keys = (distance key, column)).
 constexpr int KNN_THREADS = 256;
 constexpr int KNN_MAX_K = 1024;
+constexpr int KNN_CAP = 4096;     // candidates the fast path can hold (32 KB of shared memory)
+constexpr int KNN_SAMPLE = 8192;  // entries of the row sampled for the fast path's threshold
 
 __device__ __forceinline__ unsigned fkey(float v) {
     const unsigned b = __float_as_uint(v);
@@ -152,6 +162,148 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const void* __restrict
         const float v = (float)row[j];
         return (v != v) ? 0xFFFFFFFFu : fkey(v);
     };
+    // ---------------- fast path ----------------
+    {
+        unsigned* samp = reinterpret_cast<unsigned*>(knn_items);
+        const int S = (int)min((int64_t)KNN_SAMPLE, ncols);
+        const bool whole = (int64_t)S == ncols;
+        const int64_t run_stride = ncols / 64;  // >= 128 when the row is longer than the sample
+        for (int q = tid; q < S; q += KNN_THREADS) {
+            const int64_t j = whole ? (int64_t)q : (int64_t)(q >> 7) * run_stride + (q & 127);
+            samp[q] = (j == self) ? 0xFFFFFFFFu : key_of(j);
+        }
+        if (tid == 0) {
+            s_prefix = 0u;
+            s_mask = 0u;
+            // rank in the sample: the k-th entry itself when the sample is the row, else twice the expected rank
+            s_need = whole ? (unsigned)k : (unsigned)min(S, (int)((2.0 * (double)k * (double)S) / (double)ncols) + 17);
+        }
+        __syncthreads();
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            hist[tid] = 0u;
+            __syncthreads();
+            const unsigned prefix = s_prefix, mask = s_mask;
+            for (int q0 = 0; q0 < S; q0 += KNN_THREADS) {
+                const int q = q0 + tid;
+                unsigned bin = 0xFFFFFFFFu;
+                if (q < S) {
+                    const unsigned key = samp[q];
+                    if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+                }
+                const unsigned active = __ballot_sync(0xFFFFFFFFu, bin != 0xFFFFFFFFu);
+                if (bin != 0xFFFFFFFFu) {
+                    const unsigned peers = __match_any_sync(active, bin);
+                    if ((tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned need = s_need, acc = 0u;
+                int b = 0;
+                for (; b < 255; ++b) {
+                    if (acc + hist[b] >= need) break;
+                    acc += hist[b];
+                }
+                s_need = need - acc;
+                s_prefix = prefix | ((unsigned)b << shift);
+                s_mask = mask | (255u << shift);
+            }
+            __syncthreads();
+        }
+        const unsigned tau = s_prefix;
+        if (tid == 0) s_below = 0u;
+        __syncthreads();  // everybody has read the threshold; the sample buffer becomes the candidate buffer
+        // warp-collective append of the lanes' entries that pass the threshold (order in the buffer is irrelevant)
+        auto push = [&](bool take, unsigned key, int64_t j) {
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, take);
+            if (m) {
+                unsigned base = 0u;
+                if ((tid & 31) == __ffs(m) - 1) base = atomicAdd(&s_below, (unsigned)__popc(m));
+                base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+                const unsigned pos = base + __popc(m & ((1u << (tid & 31)) - 1u));
+                if (take && pos < (unsigned)KNN_CAP) knn_items[pos] = ((unsigned long long)key << 32) | (unsigned)j;
+            }
+        };
+        // 16-byte loads, four per thread in flight; the append runs only for the warps that saw a passing entry
+        constexpr int VEC = 16 / (int)sizeof(T);
+        constexpr int UN = 4;
+        int64_t head = 0;
+        if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+            const int64_t nvec = ncols / VEC;
+            const uint4* row4 = reinterpret_cast<const uint4*>(row);
+            for (int64_t v0 = 0; v0 < nvec; v0 += (int64_t)KNN_THREADS * UN) {
+                uint4 raw[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int64_t v = v0 + (int64_t)u * KNN_THREADS + tid;
+                    raw[u] = (v < nvec) ? __ldg(row4 + v) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int64_t v = v0 + (int64_t)u * KNN_THREADS + tid;
+                    const T* e = reinterpret_cast<const T*>(&raw[u]);
+                    unsigned keys[VEC];
+                    bool takes[VEC], any = false;
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) {
+                        const float x = (float)e[c];
+                        keys[c] = (x != x) ? 0xFFFFFFFFu : fkey(x);
+                        takes[c] = v < nvec && keys[c] <= tau && v * VEC + c != self;
+                        any |= takes[c];
+                    }
+                    if (__any_sync(0xFFFFFFFFu, any)) {
+#pragma unroll
+                        for (int c = 0; c < VEC; ++c) push(takes[c], keys[c], v * VEC + c);
+                    }
+                }
+            }
+            head = nvec * VEC;
+        }
+        for (int64_t j0 = head; j0 < ncols; j0 += KNN_THREADS) {
+            const int64_t j = j0 + tid;
+            unsigned key = 0xFFFFFFFFu;
+            bool take = false;
+            if (j < ncols && j != self) {
+                key = key_of(j);
+                take = key <= tau;
+            }
+            push(take, key, j);
+        }
+        __syncthreads();
+        const unsigned count = s_below;
+        if (count >= (unsigned)k && count <= (unsigned)KNN_CAP) {
+            int sz = 2;
+            while (sz < (int)count) sz <<= 1;
+            for (int q = (int)count + tid; q < sz; q += KNN_THREADS) knn_items[q] = ~0ull;
+            __syncthreads();
+            for (int size = 2; size <= sz; size <<= 1) {
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (int q = tid; q < sz; q += KNN_THREADS) {
+                        const int partner = q ^ stride;
+                        if (partner > q) {
+                            const bool up = (q & size) == 0;
+                            const unsigned long long a = knn_items[q], b = knn_items[partner];
+                            if ((a > b) == up) {
+                                knn_items[q] = b;
+                                knn_items[partner] = a;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int q = tid; q < k; q += KNN_THREADS) {
+                const unsigned long long it = knn_items[q];
+                const int col = (int)(unsigned)(it & 0xFFFFFFFFull);
+                out_idx[i * k + q] = col;
+                out_dist[i * k + q] = (float)row[col];
+            }
+            return;
+        }
+        __syncthreads();
+    }
+    // ---------------- exact path ----------------
     if (tid == 0) {
         s_prefix = 0u;
         s_mask = 0u;
@@ -328,7 +480,7 @@ int po_matrix_knn(const void* d_D, int64_t ld, int dtype, int64_t n_rows, int64_
     if (n_rows == 0) return PO_OK;
     int kpad = 2;
     while (kpad < k) kpad <<= 1;
-    const size_t smem = (size_t)kpad * 8;
+    const size_t smem = (size_t)(kpad > KNN_CAP ? kpad : KNN_CAP) * 8;  // candidates of the fast path / items of the exact path
     if (dtype == PO_F32)
         knn_kernel<float><<<(unsigned)n_rows, KNN_THREADS, smem, (cudaStream_t)stream>>>(d_D, ld, n_cols, self0, k, kpad, d_idx, d_dist);
     else

@@ -102,6 +102,35 @@ def test_knn_ties_go_by_column_and_nan_sorts_last():
         phyloselect.knn_graph(D, 9)
 
 
+@pytest.mark.parametrize("kind", ["smooth", "quantised", "runs", "nan_rows"])
+def test_knn_wide_rows_sampled_threshold_and_fallback(kind):
+    """Rows longer than the 8192-entry sample: the one-pass threshold path, and the rows that must fall back
+    to the exact five-pass select (thousands of ties at the threshold, small values hidden between the sampled
+    runs, rows that are mostly NaN).  Expected: stable argsort of the row with its own column removed."""
+    rng = np.random.default_rng(11)
+    rows, n, k, r0 = 24, 30000, 301, 100
+    D = rng.random((rows, n), dtype=np.float32)
+    if kind == "quantised":
+        D = np.floor(D * 4.0).astype(np.float32)  # 7500 ties per level
+    elif kind == "runs":
+        D += 1.0
+        D[:, 200:200 + 2 * k] = rng.random((rows, 2 * k), dtype=np.float32)  # all k smallest in one stretch
+        D[5, :] = 2.0
+        D[5, 29000:29000 + k + 3] = np.arange(k + 3, dtype=np.float32)[::-1] / 1000.0
+    elif kind == "nan_rows":
+        D[::2, 400:] = np.nan
+        D[3, :] = np.nan
+    idx, dist = phyloselect.knn_graph(torch.from_numpy(D).cuda(), k, row0=r0)
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    for i in range(rows):
+        row = D[i].astype(np.float64)
+        key = np.where(np.isnan(row), np.inf, row)
+        order = np.lexsort((np.arange(n), np.isnan(row), key))
+        order = order[order != r0 + i][:k]
+        assert np.array_equal(idx[i], order), (kind, i)
+        assert np.array_equal(dist[i], D[i][order], equal_nan=True), (kind, i)
+
+
 def test_command_line_front_half(tmp_path, capsys):
     seqs = synth.make_sequences(150, 3000, seed=9)
     fasta = os.path.join(tmp_path, "asm.fa")
