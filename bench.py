@@ -675,7 +675,7 @@ def run_ours(args):
             # every panel's finished blocks (its rows right of the diagonal + the mirrored column block
             # below) leave for the host matrix while the next panel computes
             return engine.matrix_to_host(None, "JSD", host_result, torch.float32, panel, prepared=(P, aux, dim),
-                                         device_matrix=matrix)
+                                         device_matrix=matrix, stats=e2e_stats)
         if symmetric:
             # panel p is complete once computed (earlier panels mirrored its left part): copy it out
             # on the copy stream while panel p+1 computes
@@ -713,6 +713,7 @@ def run_ours(args):
         distance_panels(X, d2h=False)
 
     e2e_bytes = {"h2d": 0, "d2h": 0}
+    e2e_stats = {}  # engine.matrix_to_host: bytes over PCIe / bytes the host mirrored from what had arrived
 
     def step_e2e():
         # host: index this rank's FASTA bytes; H2D: text + index; kernels; D2H: every panel
@@ -780,7 +781,7 @@ def run_ours(args):
     e2e_value = pairs_unique / float(e2e_s.item())
     if host_result is not None:  # the host copy is the device result (spot check, outside the timed region)
         torch.cuda.synchronize()
-        picks = sorted(set(int(v) for v in np.linspace(0, host_rows_n - 1, 7)))
+        picks = sorted(set(int(v) for v in np.linspace(0, host_rows_n - 1, 41)))
         for r in picks:
             assert torch.equal(host_result[r], matrix[r].cpu()), "end-to-end host matrix differs from the device matrix in row %d" % r
     io_bytes = torch.tensor([e2e_bytes["h2d"], e2e_bytes["d2h"]], dtype=torch.float64, device=device)
@@ -833,6 +834,12 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         prof_bytes = shard_bytes + n_local * DIM * 4
         prof_gbs = prof_bytes / (prof_ms / max(1, prof_n) * 1e-3) / 1e9 if prof_ms > 0 else 0.0
+        mirror_note = ""
+        if e2e_stats.get("host_mirrored_bytes"):
+            mirror_note = ("; %.1f GB of the entries left of the diagonal (share %.2f of every panel's mirrored column block) are "
+                           "not copied but transposed on the host from the blocks that have arrived, by %d threads "
+                           "(po_host_mirror_*), released in stream order, inside the timed region"
+                           % (e2e_stats["host_mirrored_bytes"] / 1e9, engine.default_host_mirror_share(), e2e_stats["mirror_threads"]))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -846,13 +853,18 @@ def run_ours(args):
                                "transposed off-diagonal tiles %s" % (world, "stored by the tile kernel into the owner's rows over NVLink "
                                "(CUDA IPC peer memory)" if peer_exchange else "exchanged over NCCL send/recv"),
                 "e2e_sink": ("the result matrix in pinned host memory (%.1f GB per rank); finished blocks leave by strided "
-                             "DMA (po_copy2d_async) while the next panel computes" % (host_bytes / 1e9)) if had_host_result
+                             "DMA (po_copy2d_async) while the next panel computes%s" % (host_bytes / 1e9, mirror_note)) if had_host_result
                             else "row panels of %d rows copied D2H into a 2-slot pinned ring (discard sink)" % panel,
             },
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(io_bytes[0].item()),
-                    "d2h_bytes_per_step": int(io_bytes[1].item()), "ms_per_step": float(e2e_s.item()) * 1e3},
+                    "d2h_bytes_per_step": int(io_bytes[1].item()), "ms_per_step": float(e2e_s.item()) * 1e3,
+                    # entries left of the diagonal that did not cross PCIe: host threads transposed them from the
+                    # blocks that had arrived (po_host_mirror_*), inside the timed region
+                    "host_mirrored_bytes_per_step": int(e2e_stats.get("host_mirrored_bytes", 0)),
+                    "host_mirror_threads": int(e2e_stats.get("mirror_threads", 0)),
+                    "host_result_bytes": int(host_bytes) if had_host_result else 0},
             "gpu_launches": int(launches),
             "roofline": {
                 "kernel": "jsd_tile_kernel<float>", "bound": "fp32",

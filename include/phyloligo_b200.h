@@ -285,6 +285,14 @@ int po_savetxt_host(const char* path, const void* h_data, int64_t rows, int64_t 
  *   po_host_transpose_f32 h_dst[c * ld_dst + r] = h_src[r * ld_src + c], float32: the mirrored block
  *                         of a block that has already arrived (the matrix is symmetric), so that only
  *                         the part on and right of the diagonal needs to cross PCIe
+ *   po_host_mirror_*      the same, asynchronous and in stream order: _open starts a pool of host threads
+ *                         (NULL on failure); _submit queues one block -- with after_stream != 0 the block is
+ *                         released to the pool by a host callback once everything enqueued on `stream`
+ *                         before the call (the DMA that brings h_src) has completed, with 0 at once; _wait
+ *                         blocks until every submitted block is written; _close waits, then joins the pool.
+ *                         The reference assigns every entry of its block row (output[s] = ...,
+ *                         bin/phyloligo.py:202-222); this is how the entries left of the diagonal get there
+ *                         without crossing PCIe.
  */
 int po_host_prefault(void* h_ptr, int64_t bytes, int threads);
 int po_host_register(void* h_ptr, int64_t bytes);
@@ -296,6 +304,11 @@ int po_host_pwrite2d(int fd, int64_t file_offset, int64_t file_pitch, const void
 int po_host_pread(int fd, int64_t file_offset, void* h_dst, int64_t bytes, int threads);
 int po_host_transpose_f32(float* h_dst, int64_t ld_dst, const float* h_src, int64_t ld_src, int64_t rows,
                           int64_t cols, int threads);
+void* po_host_mirror_open(int threads);
+int po_host_mirror_submit(void* h_pool, po_stream_t stream, int after_stream, float* h_dst, int64_t ld_dst,
+                          const float* h_src, int64_t ld_src, int64_t rows, int64_t cols);
+int po_host_mirror_wait(void* h_pool);
+int po_host_mirror_close(void* h_pool);
 
 /*
  * The front half of phyloselect.py (bin/phyloselect.py) on the device: what its K-medoids loop and

@@ -29,6 +29,7 @@ EXPORTED = [
     "po_ipc_export", "po_ipc_open", "po_ipc_close", "po_savetxt_host", "po_copy2d_async", "po_window_count_byte", "po_window_distances",
     "po_host_prefault", "po_host_register", "po_host_unregister", "po_host_copy2d", "po_host_pwrite2d",
     "po_host_pread", "po_host_transpose_f32",
+    "po_host_mirror_open", "po_host_mirror_submit", "po_host_mirror_wait", "po_host_mirror_close",
     "po_matrix_rowsums", "po_matrix_argmin_rows", "po_cluster_argmin", "po_matrix_knn", "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read", "po_microbench",
 ]
 
@@ -105,6 +106,14 @@ def load():
     lib.po_host_pread.restype = i32
     lib.po_host_transpose_f32.argtypes = [vp, i64, vp, i64, i64, i64, i32]
     lib.po_host_transpose_f32.restype = i32
+    lib.po_host_mirror_open.argtypes = [i32]
+    lib.po_host_mirror_open.restype = vp
+    lib.po_host_mirror_submit.argtypes = [vp, vp, i32, vp, i64, vp, i64, i64, i64]
+    lib.po_host_mirror_submit.restype = i32
+    lib.po_host_mirror_wait.argtypes = [vp]
+    lib.po_host_mirror_wait.restype = i32
+    lib.po_host_mirror_close.argtypes = [vp]
+    lib.po_host_mirror_close.restype = i32
     lib.po_matrix_rowsums.argtypes = [vp, i64, i32, vp, i64, i64, vp, vp, vp, vp]
     lib.po_matrix_rowsums.restype = i32
     lib.po_matrix_argmin_rows.argtypes = [vp, i64, i32, vp, i32, i64, vp, vp]

@@ -9,53 +9,23 @@
 // ring and a pool of host threads moves them (po_host_copy2d into the mapping, or
 // po_host_pwrite2d through the page cache, which never takes a page fault).  Fresh pages of
 // the output file are instantiated ahead of the copies by po_host_prefault.
-// po_host_transpose_f32 is the host half of "ship the upper triangle only": the part of the
-// matrix left of the diagonal is the transpose of what has already arrived.
+// The host half of "ship the upper triangle only" (the part of the matrix left of the diagonal is
+// the transpose of what has already arrived) lives in po_host_mirror.cu.
 #include <errno.h>
 #include <fcntl.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <unistd.h>
-#include <xmmintrin.h>
 #include <algorithm>
 #include <atomic>
 #include <thread>
 #include <vector>
 #include "po_common.cuh"
+#include "po_host_threads.h"
 
 #ifndef MADV_POPULATE_WRITE
 #define MADV_POPULATE_WRITE 23
 #endif
-
-namespace po {
-
-static int pick_threads(int threads, int64_t work_bytes) {
-    if (threads <= 0) {
-        threads = (int)std::thread::hardware_concurrency();
-        if (threads <= 0) threads = 1;
-    }
-    if (threads > 256) threads = 256;
-    // below ~1 MB per thread the start-up of a thread costs more than it moves
-    const int64_t useful = work_bytes / (1 << 20) + 1;
-    if ((int64_t)threads > useful) threads = (int)useful;
-    return threads;
-}
-
-// run fn(t) for t in [0, threads) on `threads` host threads (the caller's thread is one of them)
-template <typename F>
-static void run_threads(int threads, F fn) {
-    if (threads <= 1) {
-        fn(0);
-        return;
-    }
-    std::vector<std::thread> pool;
-    pool.reserve((size_t)threads - 1);
-    for (int t = 1; t < threads; ++t) pool.emplace_back(fn, t);
-    fn(0);
-    for (auto& th : pool) th.join();
-}
-
-}  // namespace po
 
 using namespace po;
 
@@ -217,55 +187,6 @@ int po_host_pread(int fd, int64_t file_offset, void* h_dst, int64_t bytes, int t
         set_error("po_host_pread: pread failed: %s", strerror(failed.load()));
         return PO_ERR_ARG;
     }
-    return PO_OK;
-}
-
-int po_host_transpose_f32(float* h_dst, int64_t ld_dst, const float* h_src, int64_t ld_src, int64_t rows,
-                          int64_t cols, int threads) {
-    if (rows < 0 || cols < 0 || ld_src < cols || ld_dst < rows) {
-        set_error("po_host_transpose_f32: bad geometry");
-        return PO_ERR_ARG;
-    }
-    if (rows == 0 || cols == 0) return PO_OK;
-    if (!h_dst || !h_src) {
-        set_error("po_host_transpose_f32: NULL pointer");
-        return PO_ERR_ARG;
-    }
-    // dst[c * ld_dst + r] = src[r * ld_src + c].  Tiles of 64 x 64 (16 KB in, 16 KB out: both in L1/L2),
-    // 4 x 4 register transposes inside; threads split the destination rows (= source columns) so that
-    // every thread writes whole cache lines of its own.
-    constexpr int64_t T = 64;
-    const int64_t ctiles = (cols + T - 1) / T;
-    threads = pick_threads(threads, rows * cols * 4);
-    if ((int64_t)threads > ctiles) threads = (int)ctiles;
-    run_threads(threads, [&](int t) {
-        const int64_t ct0 = ctiles * t / threads, ct1 = ctiles * (t + 1) / threads;
-        for (int64_t ct = ct0; ct < ct1; ++ct) {
-            const int64_t c0 = ct * T, c1 = std::min(cols, c0 + T);
-            for (int64_t r0 = 0; r0 < rows; r0 += T) {
-                const int64_t r1 = std::min(rows, r0 + T);
-                int64_t r = r0;
-                for (; r + 4 <= r1; r += 4) {
-                    int64_t c = c0;
-                    for (; c + 4 <= c1; c += 4) {
-                        __m128 a0 = _mm_loadu_ps(h_src + (r + 0) * ld_src + c);
-                        __m128 a1 = _mm_loadu_ps(h_src + (r + 1) * ld_src + c);
-                        __m128 a2 = _mm_loadu_ps(h_src + (r + 2) * ld_src + c);
-                        __m128 a3 = _mm_loadu_ps(h_src + (r + 3) * ld_src + c);
-                        _MM_TRANSPOSE4_PS(a0, a1, a2, a3);
-                        _mm_storeu_ps(h_dst + (c + 0) * ld_dst + r, a0);
-                        _mm_storeu_ps(h_dst + (c + 1) * ld_dst + r, a1);
-                        _mm_storeu_ps(h_dst + (c + 2) * ld_dst + r, a2);
-                        _mm_storeu_ps(h_dst + (c + 3) * ld_dst + r, a3);
-                    }
-                    for (; c < c1; ++c)
-                        for (int64_t rr = r; rr < r + 4; ++rr) h_dst[c * ld_dst + rr] = h_src[rr * ld_src + c];
-                }
-                for (; r < r1; ++r)
-                    for (int64_t c = c0; c < c1; ++c) h_dst[c * ld_dst + r] = h_src[r * ld_src + c];
-            }
-        }
-    });
     return PO_OK;
 }
 

@@ -7,6 +7,7 @@ CPU: without a CUDA device the functions raise PhyloligoError.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -454,7 +455,74 @@ def copy2d(dst, src, stream=None):
     _lib.check(rc, "po_copy2d_async")
 
 
-def matrix_to_host(X, metric, host, out_dtype=torch.float32, panel_rows=4096, prepared=None, device_matrix=None):
+class HostMirror:
+    """A pool of host threads that builds mirrored blocks of a symmetric float32 matrix in host memory, in
+    stream order (po_host_mirror_*): ``submit(dst, src, stream)`` queues ``dst[...] = src.T`` and the pool
+    starts on it once everything enqueued on `stream` before the call (the DMA that brings `src`) has
+    completed; ``wait()`` blocks until every submitted block is written."""
+
+    def __init__(self, threads=0):
+        self.lib = _lib.load()
+        self.threads = int(threads) if int(threads) > 0 else (os.cpu_count() or 1)
+        self.handle = self.lib.po_host_mirror_open(self.threads)
+        if not self.handle:
+            raise PhyloligoError("po_host_mirror_open: " + self.lib.po_last_error().decode(errors="replace"))
+
+    def submit(self, dst, src, stream=None, after_stream=True):
+        if (dst.dtype != torch.float32 or src.dtype != torch.float32 or dst.dim() != 2 or src.dim() != 2
+                or dst.shape[0] != src.shape[1] or dst.shape[1] != src.shape[0] or dst.is_cuda or src.is_cuda):
+            raise PhyloligoError("HostMirror.submit: dst and src must be 2-D float32 host views, dst.shape == src.T.shape")
+        rows, cols = int(src.shape[0]), int(src.shape[1])
+        if rows == 0 or cols == 0:
+            return
+        if (cols > 1 and src.stride(1) != 1) or (rows > 1 and dst.stride(1) != 1):
+            raise PhyloligoError("HostMirror.submit: rows must be contiguous")
+        st = C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream) if after_stream else None
+        rc = self.lib.po_host_mirror_submit(self.handle, st, 1 if after_stream else 0, _ptr(dst), int(dst.stride(0)),
+                                            _ptr(src), int(src.stride(0)), rows, cols)
+        _lib.check(rc, "po_host_mirror_submit")
+
+    def wait(self):
+        _lib.check(self.lib.po_host_mirror_wait(self.handle), "po_host_mirror_wait")
+
+    def close(self):
+        if self.handle:
+            self.lib.po_host_mirror_close(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+_MIRRORS = {}
+
+
+def host_mirror_pool(threads=None):
+    """The process-wide HostMirror with `threads` threads (default: PO_HOST_MIRROR_THREADS, else all cores but
+    two -- the CUDA callback thread and the thread that drives the device want one each)."""
+    if threads is None:
+        threads = int(os.environ.get("PO_HOST_MIRROR_THREADS", "0")) or max(1, len(os.sched_getaffinity(0)) - 2)
+    pool = _MIRRORS.get(threads)
+    if pool is None or not pool.handle:
+        pool = _MIRRORS[threads] = HostMirror(threads)
+    return pool
+
+
+def default_host_mirror_share():
+    """Share of every panel's mirrored column block that the host builds (the rest crosses PCIe):
+    PO_HOST_MIRROR in [0, 1]."""
+    return min(1.0, max(0.0, float(os.environ.get("PO_HOST_MIRROR", "%r" % HOST_MIRROR_DEFAULT))))
+
+
+# Measured on the B200 hosts of this pool (16 cores, PCIe 52 GB/s, tools/e2e_mirror_sweep.py): see DESIGN.md 6.1
+HOST_MIRROR_DEFAULT = 1.0
+
+
+def matrix_to_host(X, metric, host, out_dtype=torch.float32, panel_rows=4096, prepared=None, device_matrix=None,
+                   host_mirror=None, mirror_threads=None, stats=None):
     """The whole symmetric n x n matrix of profiles X into the host tensor `host` (n x n, pinned).
 
     The device keeps the matrix resident (4 n^2 bytes); row panels are computed top to bottom, upper
@@ -463,7 +531,16 @@ def matrix_to_host(X, metric, host, out_dtype=torch.float32, panel_rows=4096, pr
     mirrored column block [r1, n) x [r0, r1) below it.  What has become final is always
     proportional to what has been computed, so the PCIe link never waits for the expensive
     top panels (copying whole rows only, the first third of the matrix runs at kernel speed
-    and the link idles).  Returns the number of bytes copied to the host."""
+    and the link idles).
+
+    The mirrored column block is the transpose of the part of the panel right of its diagonal block,
+    which has just arrived in `host`: a share `host_mirror` of it (its bottom rows; float32 only;
+    default ``default_host_mirror_share()``) is not copied but built there by the threads of a
+    HostMirror pool, released in stream order by a callback behind the panel's DMA -- 40 GB over a
+    52 GB/s link is what bounds the step otherwise, the kernels need 0.5 s.  The call returns when the
+    DMA is enqueued and the host's share is written (the pool is waited for); the caller synchronises
+    the device as before.  Returns the number of bytes copied to the host over PCIe; `stats`, when
+    given, receives {"dma_bytes", "host_mirrored_bytes", "mirror_threads"}."""
     device = require_cuda()
     P, aux, dim = prepared if prepared is not None else prepare(X, metric)
     n = int(P.shape[0])
@@ -472,10 +549,15 @@ def matrix_to_host(X, metric, host, out_dtype=torch.float32, panel_rows=4096, pr
     full = device_matrix if device_matrix is not None else torch.empty((n, n), dtype=out_dtype, device=device)
     if tuple(full.shape) != (n, n) or full.dtype != out_dtype:
         raise PhyloligoError("matrix_to_host: device_matrix must be (n, n) of the output dtype")
+    share = default_host_mirror_share() if host_mirror is None else min(1.0, max(0.0, float(host_mirror)))
+    if out_dtype != torch.float32 or host.stride(1) != 1:
+        share = 0.0
+    pool = host_mirror_pool(mirror_threads) if share > 0.0 else None
     step = max(TILE, (int(panel_rows) // TILE) * TILE)
     compute = torch.cuda.current_stream()
     copy_stream = torch.cuda.Stream()
     copied = 0
+    mirrored = 0
     for r0 in range(0, n, step):
         r1 = min(n, r0 + step)
         distance_block(metric, P, aux, dim, r0, r1, 0, n, full, 0, 0, FLAG_SKIP_LOWER | FLAG_MIRROR)
@@ -483,10 +565,19 @@ def matrix_to_host(X, metric, host, out_dtype=torch.float32, panel_rows=4096, pr
         ready.record(compute)
         copy_stream.wait_event(ready)
         copy2d(host[r0:r1, r0:], full[r0:r1, r0:], copy_stream)
-        copy2d(host[r1:, r0:r1], full[r1:, r0:r1], copy_stream)
-        copied += ((r1 - r0) * (n - r0) + (n - r1) * (r1 - r0)) * full.element_size()
+        # rows [r1, rs) of the mirrored column block by DMA, rows [rs, n) by the host from host[r0:r1, rs:]
+        rs = n - int(round(share * (n - r1))) if pool is not None else n
+        if rs < n:
+            pool.submit(host[rs:, r0:r1], host[r0:r1, rs:], copy_stream)
+            mirrored += (n - rs) * (r1 - r0) * full.element_size()
+        copy2d(host[r1:rs, r0:r1], full[r1:rs, r0:r1], copy_stream)
+        copied += ((r1 - r0) * (n - r0) + (rs - r1) * (r1 - r0)) * full.element_size()
     compute.wait_stream(copy_stream)
     full.record_stream(copy_stream)
+    if pool is not None:
+        pool.wait()
+    if stats is not None:
+        stats.update(dma_bytes=copied, host_mirrored_bytes=mirrored, mirror_threads=pool.threads if pool else 0)
     return copied
 
 

@@ -281,19 +281,51 @@ def test_tensor_core_spearman_is_exact(n, dim, monkeypatch):
 
 
 @pytest.mark.parametrize("metric,n", [("JSD", 700), ("EuclGram", 520), ("SC", 300)])
-def test_matrix_to_host_ships_finished_blocks(metric, n):
-    """engine.matrix_to_host: panels' right parts + mirrored column blocks by strided DMA
-    (po_copy2d_async) give exactly the resident matrix in pinned host memory."""
+@pytest.mark.parametrize("share", [0.0, 0.4, 1.0])
+def test_matrix_to_host_ships_finished_blocks(metric, n, share):
+    """engine.matrix_to_host: panels' right parts by strided DMA (po_copy2d_async), the mirrored column
+    blocks partly by DMA and partly built on the host from what has arrived (po_host_mirror_*, released in
+    stream order): exactly the resident matrix in pinned host memory, whatever the split."""
     rng = np.random.default_rng(n)
     X = torch.from_numpy(rng.dirichlet(np.ones(256), size=n).astype(np.float32)).cuda()
     want = engine.distance_matrix_device(X, metric, torch.float32, symmetric=True).cpu()
     host = torch.full((n, n), -1.0, dtype=torch.float32).pin_memory()
-    copied = engine.matrix_to_host(X, metric, host, torch.float32, panel_rows=128)
+    stats = {}
+    copied = engine.matrix_to_host(X, metric, host, torch.float32, panel_rows=128, host_mirror=share, mirror_threads=3,
+                                   stats=stats)
     torch.cuda.synchronize()
-    assert copied == n * n * 4
+    assert copied == stats["dma_bytes"] and copied + stats["host_mirrored_bytes"] == n * n * 4
+    if share == 0.0:
+        assert stats["host_mirrored_bytes"] == 0
+    if share == 1.0:
+        tri = sum((min(n, r0 + 128) - r0) * (n - r0) for r0 in range(0, n, 128)) * 4
+        assert copied == tri
     assert torch.equal(host, want)
     with pytest.raises(Exception):
         engine.matrix_to_host(X, metric, torch.empty((n, n), dtype=torch.float32), torch.float32)  # not pinned
+
+
+def test_matrix_to_host_float64_goes_by_dma_only():
+    X = torch.from_numpy(np.random.default_rng(3).dirichlet(np.ones(64), size=300).astype(np.float32)).cuda()
+    want = engine.distance_matrix_device(X, "JSD", torch.float64, symmetric=True).cpu()
+    host = torch.zeros((300, 300), dtype=torch.float64).pin_memory()
+    stats = {}
+    engine.matrix_to_host(X, "JSD", host, torch.float64, panel_rows=128, host_mirror=1.0, stats=stats)
+    torch.cuda.synchronize()
+    assert stats["host_mirrored_bytes"] == 0 and torch.equal(host, want)
+
+
+def test_host_mirror_repeated_steps_reuse_the_pool():
+    """Back-to-back steps into the same host matrix (what bench.py's e2e loop does): every step's result is
+    complete when the call returns and the device is synchronised."""
+    n = 900
+    host = torch.zeros((n, n), dtype=torch.float32).pin_memory()
+    for seed in range(4):
+        X = torch.from_numpy(np.random.default_rng(seed).dirichlet(np.ones(256), size=n).astype(np.float32)).cuda()
+        engine.matrix_to_host(X, "JSD", host, torch.float32, panel_rows=256, host_mirror=1.0)
+        torch.cuda.synchronize()
+        want = engine.distance_matrix_device(X, "JSD", torch.float32, symmetric=True).cpu()
+        assert torch.equal(host, want), seed
 
 
 def test_copy2d_strided_views():

@@ -40,6 +40,76 @@ def test_transpose(lib, rows, cols):
     assert np.array_equal(out[:, :rows], a[:, :cols].T) and (out[:, rows:] == -1).all()
 
 
+def _aligned_f32(n, align=64, fill=None):
+    raw = np.empty(n * 4 + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    a = raw[off:off + n * 4].view(np.float32)
+    if fill is not None:
+        a[:] = fill
+    return a
+
+
+@pytest.mark.parametrize("rows,cols,ld_dst,col_off,row_off", [
+    (24, 8, 32, 0, 0),          # the smallest block the vector path takes
+    (200, 130, 256, 0, 0),      # pitch % 16 == 0: 64-byte phase, ragged rows and columns
+    (200, 130, 264, 0, 0),      # pitch % 8 == 0 only: 32-byte phase
+    (333, 97, 512, 5, 3),       # destination and source start off the alignment grid
+    (333, 97, 520, 7, 1),
+    (129, 64, 257, 0, 0),       # odd pitch: the scalar / SSE form
+    (1024, 4096 - 64, 1056, 16, 0),
+])
+def test_transpose_vector_path_alignments(lib, rows, cols, ld_dst, col_off, row_off):
+    """The AVX2 form (streaming stores, aligned from the first row whose address allows it) against numpy,
+    for every alignment case: nothing outside the destination block may change."""
+    rng = np.random.default_rng(rows * 31 + cols)
+    ld_src = cols + 11
+    src = _aligned_f32(rows * ld_src + row_off)[row_off:]
+    src[:] = rng.random(src.shape[0]).astype(np.float32)
+    S = src[: rows * ld_src].reshape(rows, ld_src)
+    assert ld_dst >= rows + col_off
+    dst = _aligned_f32((cols + 2) * ld_dst, fill=-7.0)
+    D = dst.reshape(cols + 2, ld_dst)
+    target = D[1:, col_off:]
+    rc = lib.po_host_transpose_f32(target.ctypes.data, ld_dst, S.ctypes.data, ld_src, rows, cols, 4)
+    assert rc == 0
+    assert np.array_equal(D[1:cols + 1, col_off:col_off + rows], S[:, :cols].T)
+    D[1:cols + 1, col_off:col_off + rows] = -7.0
+    assert (dst == -7.0).all()
+
+
+def test_mirror_pool_builds_lower_triangle(lib):
+    """po_host_mirror_*: blocks submitted for immediate release (no stream) are transposed by the pool;
+    the lower triangle of a symmetric matrix is rebuilt panel by panel from its upper triangle."""
+    n, panel = 1000, 128
+    rng = np.random.default_rng(5)
+    full = rng.random((n, n)).astype(np.float32)
+    full = np.triu(full) + np.triu(full, 1).T
+    host = _aligned_f32(n * n).reshape(n, n)
+    host[:] = np.triu(full)
+    pool = lib.po_host_mirror_open(3)
+    assert pool
+    for r0 in range(0, n, panel):
+        r1 = min(n, r0 + panel)
+        if r1 == n:
+            break
+        dst, src = host[r1:, r0:r1], host[r0:r1, r1:]
+        rc = lib.po_host_mirror_submit(pool, None, 0, dst.ctypes.data, n, src.ctypes.data, n, r1 - r0, n - r1)
+        assert rc == 0
+    assert lib.po_host_mirror_wait(pool) == 0
+    assert lib.po_host_mirror_wait(pool) == 0  # idempotent
+    # the diagonal blocks' lower halves were not submitted: mirror them here
+    for r0 in range(0, n, panel):
+        r1 = min(n, r0 + panel)
+        blk = host[r0:r1, r0:r1]
+        blk[:] = np.triu(blk) + np.triu(blk, 1).T
+    assert np.array_equal(host, full)
+    assert lib.po_host_mirror_submit(pool, None, 0, host.ctypes.data, 4, host.ctypes.data, 4, 8, 8) < 0  # pitch < extent
+    assert b"geometry" in lib.po_last_error()
+    assert lib.po_host_mirror_submit(pool, None, 0, None, 8, None, 8, 0, 8) == 0  # empty block: nothing to do
+    assert lib.po_host_mirror_close(pool) == 0
+    assert lib.po_host_mirror_close(None) == 0
+
+
 def test_file_matrix_create_attach_warm(tmp_path):
     path = os.path.join(tmp_path, "d.mat")
     with hostsink.FileMatrix(path, 300, 300, np.float32, create=True) as fm:
