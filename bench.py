@@ -618,20 +618,66 @@ def run_ours(args):
     except Exception:
         avail = 0
     host_result = None
-    if not args.ring_sink and host_bytes * world < 0.5 * avail:
+    shared_host = None   # world > 1: (FileMatrix, n x n host tensor every rank maps, MirroredHostSink pool)
+    if world > 1 and not args.ring_sink and not os.environ.get("PO_BENCH_RANK_ROWS") and n_contigs * n_contigs * 4 < 0.5 * avail:
+        # One n x n matrix in shared memory that every rank maps; a rank page-locks its own rows (the DMA
+        # target).  Only the parts of the block rows on and right of the diagonal cross PCIe; the rank that
+        # shipped a block transposes it into the rows below (multigpu.MirroredHostSink).
+        from phyloligo_b200 import hostsink
+        shm_dir2 = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        e2e_path = os.path.join(shm_dir2, "phyloligo_bench_e2e_%s_%d.mat" % (os.environ.get("MASTER_PORT", "0"), n_contigs))
+        ok = 1
+        fm = None
+        if rank == 0:
+            try:
+                fm = hostsink.FileMatrix(e2e_path, n_contigs, n_contigs, np.float32, create=True)
+                os.posix_fallocate(fm.fd, 0, fm.nbytes)
+            except Exception as exc:
+                print("bench: no shared host matrix (%s)" % exc, file=sys.stderr)
+                ok = 0
+        dist.barrier()  # the file exists (or rank 0 has given up: the all-reduce below tells everybody)
+        try:
+            if rank != 0:
+                fm = hostsink.FileMatrix(e2e_path, n_contigs, n_contigs, np.float32, create=False)
+            own = [ranges[i] for i in sharding.owned_ranges(ranges, rank, world) if ranges[i][1] > ranges[i][0]]
+            if ok and not fm.register_rows(own):
+                print("bench: rank %d cannot page-lock its rows of the shared host matrix (%s)"
+                      % (rank, _lib.load().po_last_error().decode(errors="replace")), file=sys.stderr)
+                ok = 0
+        except Exception as exc:
+            print("bench: rank %d: no shared host matrix (%s)" % (rank, exc), file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            threads = int(os.environ.get("PO_HOST_MIRROR_THREADS", "0")) or max(2, -(-3 * (os.cpu_count() or 1) // (2 * world)))
+            host_all = torch.from_numpy(fm.array)
+            pool_ = engine.HostMirror(threads)
+            shared_host = (fm, host_all, pool_, multigpu.MirroredHostSink(host_all, pool_))
+        else:
+            if fm is not None:
+                fm.close()
+            fm = None
+        dist.barrier()
+        if rank == 0 and shared_host is None:
+            try:
+                os.unlink(e2e_path)
+            except OSError:
+                pass
+    if shared_host is None and not args.ring_sink and host_bytes * world < 0.5 * avail:
         try:
             host_result = torch.empty((host_rows_n, n_contigs), dtype=torch.float32).pin_memory()
         except RuntimeError as exc:  # page-locking refused (cgroup / ulimit): fall back to the panel ring
             print("bench: cannot pin %.1f GB of host memory (%s); using the ring sink" % (host_bytes / 1e9, exc),
                   file=sys.stderr)
             host_result = None
-    if world > 1:  # every rank must take the same path (the barriers inside BlockRows.compute are collective)
+    if world > 1 and shared_host is None:  # every rank must take the same path (the barriers inside BlockRows.compute are collective)
         flag = torch.tensor([1 if host_result is not None else 0], device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
             host_result = None
     pin_ring = None
-    if host_result is None:
+    if host_result is None and shared_host is None:
         pin_ring = [torch.empty((panel, n_contigs), dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     pin_begin = torch.from_numpy(np.zeros(max(1, n_local), dtype=np.int64)).pin_memory()
@@ -702,6 +748,14 @@ def run_ours(args):
             return d2h_bytes
         # multi-GPU: per owned block row the diagonal block (mirrored in place) and the blocks right of
         # it, whose transposed tiles the kernel stores into the owning rank's rows (multigpu.BlockRows)
+        if d2h and shared_host is not None:
+            sink = shared_host[3]
+            sink.reset()
+            job.compute("JSD", P, aux, dim, ship=sink.ship, left_parts=False)
+            sink.finish()
+            e2e_stats.update(dma_bytes=sink.dma_bytes, host_mirrored_bytes=sink.mirrored_bytes,
+                             mirror_threads=shared_host[2].threads)
+            return sink.dma_bytes
         if d2h and host_result is not None:
             job.compute("JSD", P, aux, dim, host_rows=host_result)
             return rows_owned * n_contigs * 4
@@ -784,7 +838,15 @@ def run_ours(args):
         picks = sorted(set(int(v) for v in np.linspace(0, host_rows_n - 1, 41)))
         for r in picks:
             assert torch.equal(host_result[r], matrix[r].cpu()), "end-to-end host matrix differs from the device matrix in row %d" % r
-    io_bytes = torch.tensor([e2e_bytes["h2d"], e2e_bytes["d2h"]], dtype=torch.float64, device=device)
+    if shared_host is not None:  # after timed()'s closing barrier every rank's share is in the shared matrix
+        torch.cuda.synchronize()
+        for i in job.my_ranges:
+            a, b = job.ranges[i]
+            for r in sorted(set(int(v) for v in np.linspace(a, b - 1, 9))):
+                assert torch.equal(shared_host[1][r], job.out_rows[i][r - a].cpu()), \
+                    "end-to-end shared host matrix differs from the device rows in row %d" % r
+    io_bytes = torch.tensor([e2e_bytes["h2d"], e2e_bytes["d2h"], e2e_stats.get("host_mirrored_bytes", 0)],
+                            dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(io_bytes, op=dist.ReduceOp.SUM)
 
@@ -800,7 +862,22 @@ def run_ours(args):
     # ---- the drop-in path itself: compute_frequencies + compute_distances(... "memmap" ...) into a real file ----
     e2e_cli = None
     peer_exchange = job is not None and job.peers is not None
-    had_host_result = host_result is not None
+    had_host_result = host_result is not None or shared_host is not None
+    had_shared_host = shared_host is not None
+    if shared_host is not None:
+        if world > 1:
+            dist.barrier()  # nobody unmaps while another rank's pool may still write into these rows
+        shared_host[2].close()
+        fm_ = shared_host[0]
+        shared_host = None
+        fm_.close()
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(e2e_path)
+            except OSError:
+                pass
     if not args.no_cli:
         sample_rows = [0, n_contigs // 3, n_contigs - 1]
         want_rows = {r: matrix_row(r) for r in sample_rows}  # collective under torchrun (all-gather of profiles)
@@ -835,7 +912,13 @@ def run_ours(args):
         prof_bytes = shard_bytes + n_local * DIM * 4
         prof_gbs = prof_bytes / (prof_ms / max(1, prof_n) * 1e-3) / 1e9 if prof_ms > 0 else 0.0
         mirror_note = ""
-        if e2e_stats.get("host_mirrored_bytes"):
+        if had_shared_host:
+            mirror_note = ("; ONE n x n matrix in shared memory mapped by every rank (own rows page-locked): only the parts of the "
+                           "block rows on and right of the diagonal cross PCIe (%.1f GB over all ranks), the rank that shipped a "
+                           "block transposes it into the rows below from host memory (%.1f GB, %d threads per rank, "
+                           "po_host_mirror_*, released in stream order, inside the timed region)"
+                           % (io_bytes[1].item() / 1e9, io_bytes[2].item() / 1e9, e2e_stats.get("mirror_threads", 0)))
+        elif e2e_stats.get("host_mirrored_bytes"):
             mirror_note = ("; %.1f GB of the entries left of the diagonal (share %.2f of every panel's mirrored column block) are "
                            "not copied but transposed on the host from the blocks that have arrived, by %d threads "
                            "(po_host_mirror_*), released in stream order, inside the timed region"
@@ -852,8 +935,10 @@ def run_ours(args):
                                "%d ranks: records sharded, NCCL all-gather of profiles, paired block rows (s, 2W-1-s), "
                                "transposed off-diagonal tiles %s" % (world, "stored by the tile kernel into the owner's rows over NVLink "
                                "(CUDA IPC peer memory)" if peer_exchange else "exchanged over NCCL send/recv"),
-                "e2e_sink": ("the result matrix in pinned host memory (%.1f GB per rank); finished blocks leave by strided "
-                             "DMA (po_copy2d_async) while the next panel computes%s" % (host_bytes / 1e9, mirror_note)) if had_host_result
+                "e2e_sink": ("the result matrix in pinned host memory (%.1f GB%s); finished blocks leave by strided "
+                             "DMA (po_copy2d_async) while the next panel computes%s"
+                             % ((n_contigs * n_contigs * 4 if had_shared_host else host_bytes) / 1e9,
+                                "" if had_shared_host else " per rank", mirror_note)) if had_host_result
                             else "row panels of %d rows copied D2H into a 2-slot pinned ring (discard sink)" % panel,
             },
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
@@ -862,9 +947,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(io_bytes[1].item()), "ms_per_step": float(e2e_s.item()) * 1e3,
                     # entries left of the diagonal that did not cross PCIe: host threads transposed them from the
                     # blocks that had arrived (po_host_mirror_*), inside the timed region
-                    "host_mirrored_bytes_per_step": int(e2e_stats.get("host_mirrored_bytes", 0)),
+                    "host_mirrored_bytes_per_step": int(io_bytes[2].item()),
                     "host_mirror_threads": int(e2e_stats.get("mirror_threads", 0)),
-                    "host_result_bytes": int(host_bytes) if had_host_result else 0},
+                    "host_result_bytes": (n_contigs * n_contigs * 4 if had_shared_host else int(host_bytes) * world) if had_host_result else 0},
             "gpu_launches": int(launches),
             "roofline": {
                 "kernel": "jsd_tile_kernel<float>", "bound": "fp32",

@@ -139,10 +139,39 @@ class FileMatrix:
             self.registered = True
         return self.registered
 
+    def register_rows(self, row_ranges):
+        """Page-lock the pages that hold the given row ranges only (a rank's own rows of a matrix every rank
+        maps): adjacent or overlapping ranges are merged, every range is widened to page boundaries.
+        False when the kernel refuses (nothing stays registered then)."""
+        if self.mm is None:
+            return False
+        page = mmap.PAGESIZE
+        spans = []
+        for r0, r1 in sorted((int(a), int(b)) for a, b in row_ranges if b > a):
+            lo, hi = self.row_bytes(r0, r1)
+            lo, hi = lo // page * page, min(self.offset + self.nbytes, -(-hi // page) * page)
+            if spans and lo <= spans[-1][1]:
+                spans[-1][1] = max(spans[-1][1], hi)
+            else:
+                spans.append([lo, hi])
+        lib = _lib.load()
+        done = []
+        for lo, hi in spans:
+            if lib.po_host_register(C.c_void_p(self.base + lo), hi - lo) != 0:
+                for a in done:
+                    lib.po_host_unregister(C.c_void_p(self.base + a))
+                return False
+            done.append(lo)
+        self._registered_spans = getattr(self, "_registered_spans", []) + done
+        return True
+
     def close(self):
         if self.warmer is not None:
             self.warmer.stop()
             self.warmer = None
+        for a in getattr(self, "_registered_spans", []):
+            _lib.load().po_host_unregister(C.c_void_p(self.base + a))
+        self._registered_spans = []
         if self.registered:
             _lib.load().po_host_unregister(C.c_void_p(self.array.ctypes.data))
             self.registered = False

@@ -103,7 +103,7 @@ class BlockRows:
     def upper_area(self):
         return sharding.upper_area(self.ranges, self.rank, self.world, self.n)
 
-    def compute(self, metric, P, aux, dim, host_rows=None, ship=None):
+    def compute(self, metric, P, aux, dim, host_rows=None, ship=None, left_parts=True):
         """Launch this rank's tiles; on return (in stream order) `matrix` holds its complete rows.
 
         With `host_rows` (a pinned [rows_owned x n] tensor) the rows also go to the host: the part of
@@ -112,7 +112,11 @@ class BlockRows:
         row's tiles; the part left of the diagonal block is written by the other ranks and leaves
         after the closing barrier.  `ship(block, row0, col0)` instead hands every such finished
         device block (a view of `matrix`, with the matrix coordinates of its corner) to the caller in
-        the same order -- the command line's file sink (hostsink.RowShipper).  Returns `matrix`."""
+        the same order -- the command line's file sink (hostsink.RowShipper).  With
+        ``left_parts=False`` only the parts from the diagonal block rightwards are handed over: the
+        caller builds the rest from them (``MirroredHostSink``: the matrix is symmetric, and the part of
+        a block row left of its diagonal block is the transpose of right parts that other ranks ship).
+        Returns `matrix`."""
         n = self.n
         if host_rows is not None:
             if tuple(host_rows.shape) != tuple(self.matrix.shape) or not host_rows.is_pinned():
@@ -168,9 +172,71 @@ class BlockRows:
             self._device_barrier()
         elif self.world > 1:
             sharding.exchange_transposed(self.staging, self.ranges, self.rank, self.world, self.out_rows)
-        if ship is not None:
+        if ship is not None and left_parts:
             for i in self.my_ranges:
                 ship_part(i, right=False)
         if host_rows is not None:
             torch.cuda.current_stream().wait_stream(self._copy_stream)
         return self.matrix
+
+
+class MirroredHostSink:
+    """The host end of a multi-GPU run that lets only the upper triangle cross PCIe.
+
+    `host` is the whole n x n float32 matrix in host memory that every rank of the node maps (a file
+    under /dev/shm: ``hostsink.FileMatrix``; a rank's own rows page-locked so that DMA lands in them).
+    ``ship`` (the callback of ``BlockRows.compute(..., ship=sink.ship, left_parts=False)``) takes the
+    part of a block row from its diagonal block rightwards, sends it to the rank's rows of `host` in
+    sub-panels of `sub_rows` rows by strided DMA, and queues behind every sub-panel the transposition
+    of its columns right of the diagonal block into the rows below (``engine.HostMirror``, released in
+    stream order) -- rows that other ranks own.  Every entry left of the diagonal is therefore written
+    by the rank that computed its mirror image, from host memory, and no rank ships the left part of
+    its rows: half of the bytes cross PCIe.  The regions the ranks write are disjoint; the matrix is
+    complete when every rank has called ``finish`` (a barrier is the caller's).  The reference's
+    workers assign whole block rows (output[s] = ..., bin/phyloligo.py:202-222)."""
+
+    def __init__(self, host, pool, sub_rows=1024):
+        if host.dim() != 2 or host.shape[0] != host.shape[1] or host.dtype != torch.float32 or host.is_cuda:
+            raise RuntimeError("MirroredHostSink: host must be a square float32 host tensor")
+        self.host, self.pool = host, pool
+        self.n = int(host.shape[0])
+        self.sub = max(1, int(sub_rows))
+        self._copy_stream = None
+        self.reset()
+
+    def reset(self):
+        """Zero the byte counters (a sink serves many steps)."""
+        self.dma_bytes = 0
+        self.mirrored_bytes = 0
+
+    def ship(self, block, row0, col0):
+        if col0 != row0 or block.shape[1] != self.n - col0:
+            raise RuntimeError("MirroredHostSink.ship: expected the part of a block row from its diagonal block rightwards")
+        h = int(block.shape[0])
+        b = row0 + h
+        on_device = block.is_cuda
+        if on_device:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream()
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream())
+            self._copy_stream.wait_event(ready)
+        for r0 in range(0, h, self.sub):
+            r1 = min(h, r0 + self.sub)
+            dst = self.host[row0 + r0:row0 + r1, col0:]
+            if on_device:
+                engine.copy2d(dst, block[r0:r1], self._copy_stream)
+            else:  # the CPU stand-in of the gloo tests
+                dst.copy_(block[r0:r1])
+            self.dma_bytes += (r1 - r0) * (self.n - col0) * 4
+            if b < self.n:
+                self.pool.submit(self.host[b:, row0 + r0:row0 + r1], self.host[row0 + r0:row0 + r1, b:],
+                                 self._copy_stream, after_stream=on_device)
+                self.mirrored_bytes += (r1 - r0) * (self.n - b) * 4
+
+    def finish(self):
+        """Stream-order the copies before whatever follows on the current stream, and wait for this rank's
+        share of the mirroring."""
+        if self._copy_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._copy_stream)
+        self.pool.wait()

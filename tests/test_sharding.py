@@ -152,6 +152,38 @@ def _block_rows_worker(rank, world, port, n, dim):
         mine = sum((r1 - r0) * (c1 - c0) for r0, r1, c0, c1 in calls)
         diag = sum((r1 - r0) ** 2 for r0, r1, c0, c1 in calls if (r0, r1) == (c0, c1))
         assert mine - diag + (diag + sum(r1 - r0 for r0, r1, c0, c1 in calls if (r0, r1) == (c0, c1))) // 2 == job.upper_area()
+        # upper triangle only across "PCIe": every rank hands the right parts of its block rows to a
+        # MirroredHostSink over ONE matrix in shared memory and transposes them into the rows below; no
+        # rank ships a left part, and together the ranks fill the whole matrix
+        import tempfile
+        from phyloligo_b200 import hostsink
+        path = os.path.join(tempfile.gettempdir(), "po_test_shared_%d.mat" % port)
+        if rank == 0:
+            fm = hostsink.FileMatrix(path, n, n, np.float32, create=True)
+            fm.array[:] = np.nan
+        dist.barrier()
+        if rank != 0:
+            fm = hostsink.FileMatrix(path, n, n, np.float32, create=False)
+        host = torch.from_numpy(fm.array)
+        pool = engine.HostMirror(2)
+        sink = multigpu.MirroredHostSink(host, pool, sub_rows=100)
+        engine.distance_block = fake_block
+        try:
+            job.compute("Eucl", None, None, dim, ship=sink.ship, left_parts=False)
+        finally:
+            engine.distance_block = keep
+        sink.finish()
+        dist.barrier()
+        assert torch.equal(host, full.float()), "rank %d: shared host matrix" % rank
+        tri = sum((job.ranges[i][1] - job.ranges[i][0]) * (n - job.ranges[i][0]) for i in job.my_ranges) * 4
+        low = sum((job.ranges[i][1] - job.ranges[i][0]) * (n - job.ranges[i][1]) for i in job.my_ranges) * 4
+        assert sink.dma_bytes == tri and sink.mirrored_bytes == low
+        dist.barrier()
+        pool.close()
+        del host, sink
+        fm.close()
+        if rank == 0:
+            os.unlink(path)
         job.close()
     finally:
         dist.destroy_process_group()
