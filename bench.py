@@ -751,13 +751,13 @@ def run_ours(args):
         if d2h and shared_host is not None:
             sink = shared_host[3]
             sink.reset()
-            job.compute("JSD", P, aux, dim, ship=sink.ship, left_parts=False)
+            job.compute("JSD", P, aux, dim, ship=sink.ship, left_parts=False, panel_rows=panel)
             sink.finish()
             e2e_stats.update(dma_bytes=sink.dma_bytes, host_mirrored_bytes=sink.mirrored_bytes,
                              mirror_threads=shared_host[2].threads)
             return sink.dma_bytes
         if d2h and host_result is not None:
-            job.compute("JSD", P, aux, dim, host_rows=host_result)
+            job.compute("JSD", P, aux, dim, host_rows=host_result, panel_rows=panel)
             return rows_owned * n_contigs * 4
         job.compute("JSD", P, aux, dim)
         return d2h_panels(matrix, rows_owned) if d2h else 0

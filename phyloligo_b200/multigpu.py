@@ -29,7 +29,7 @@ import torch
 import torch.distributed as dist
 
 from . import engine, sharding
-from ._lib import FLAG_MIRROR, FLAG_SKIP_LOWER
+from ._lib import FLAG_MIRROR, FLAG_SKIP_LOWER, TILE
 
 
 def default_exchange():
@@ -103,7 +103,7 @@ class BlockRows:
     def upper_area(self):
         return sharding.upper_area(self.ranges, self.rank, self.world, self.n)
 
-    def compute(self, metric, P, aux, dim, host_rows=None, ship=None, left_parts=True):
+    def compute(self, metric, P, aux, dim, host_rows=None, ship=None, left_parts=True, panel_rows=None):
         """Launch this rank's tiles; on return (in stream order) `matrix` holds its complete rows.
 
         With `host_rows` (a pinned [rows_owned x n] tensor) the rows also go to the host: the part of
@@ -116,7 +116,11 @@ class BlockRows:
         ``left_parts=False`` only the parts from the diagonal block rightwards are handed over: the
         caller builds the rest from them (``MirroredHostSink``: the matrix is symmetric, and the part of
         a block row left of its diagonal block is the transpose of right parts that other ranks ship).
-        Returns `matrix`."""
+        With `panel_rows` a block row is launched and shipped in row panels of that many rows (a multiple
+        of the largest tile): a panel's finished part leaves while the next panel computes, instead of a
+        whole block row's -- with two block rows per rank, the first of them most of the rank's work,
+        shipping by whole block rows serialises compute and copy.  The tiles and their values do not
+        depend on the split.  Returns `matrix`."""
         n = self.n
         if host_rows is not None:
             if tuple(host_rows.shape) != tuple(self.matrix.shape) or not host_rows.is_pinned():
@@ -133,48 +137,56 @@ class BlockRows:
                 self._copy_stream.wait_event(ready)
                 engine.copy2d(_host[off:off + block.shape[0], col0:col0 + block.shape[1]], block, self._copy_stream)
 
-        def ship_part(i, right):
+        def ship_panel(i, r0, r1):
+            """what has just become final of rows [r0, r1) of block row i"""
             a, b = self.ranges[i]
-            rows = self.out_rows[i]
-            if right:
-                ship(rows[:, a:], a, a)
-            elif a > 0:
-                ship(rows[:, :a], a, 0)
+            rows = self.out_rows[i][r0 - a:r1 - a]
+            if left_parts:
+                ship(rows[:, a:], r0, a)    # earlier panels of the block row mirrored into columns [a, r0)
+            else:
+                ship(rows[:, r0:], r0, r0)  # the caller mirrors everything right of the panel's own square
 
+        def ship_left(i):
+            a, b = self.ranges[i]
+            if a > 0:
+                ship(self.out_rows[i][:, :a], a, 0)
+
+        step = None
+        if panel_rows:
+            step = max(TILE, (int(panel_rows) // TILE) * TILE)
         if self.peers is not None:
             self._device_barrier()  # the consumers of the previous result are done with the rows
-        for k, i in enumerate(self.my_ranges):
+        for i in self.my_ranges:
             a, b = self.ranges[i]
             rows = self.out_rows[i]
-            if ship is not None and k > 0:
-                ship_part(self.my_ranges[k - 1], right=True)
-            engine.distance_block(metric, P, aux, dim, a, b, a, b, rows, a, 0, FLAG_SKIP_LOWER | FLAG_MIRROR)
-            if b >= n:
-                continue
-            if self.staging is not None:
-                engine.distance_block(metric, P, aux, dim, a, b, b, n, rows, a, 0, FLAG_MIRROR,
-                                      mirror=self.staging[i], mirror_row0=b, mirror_col0=a)
-                continue
-            # one launch per block right of the diagonal; its transposed tiles are stored into the
-            # rows of the rank that owns that range (local or peer address, row pitch n)
-            for q in range(i + 1, len(self.ranges)):
-                aq, bq = self.ranges[q]
-                if bq <= aq:
-                    continue
-                owner = sharding.range_owner(q, self.world)
-                base = self.matrix.data_ptr() if owner == self.rank else self.peers.address(owner)
-                addr = base + self.offsets[q] * n * self.esize
-                engine.distance_block(metric, P, aux, dim, a, b, aq, bq, rows, a, 0, FLAG_MIRROR,
-                                      mirror=addr, mirror_row0=aq, mirror_col0=0, mirror_ld=n)
-        if ship is not None and self.my_ranges:
-            ship_part(self.my_ranges[-1], right=True)
+            for r0 in range(a, b, step or (b - a)):
+                r1 = min(b, r0 + (step or (b - a)))
+                # the panel's part of the diagonal block: tiles on or right of the diagonal, mirrored in place
+                engine.distance_block(metric, P, aux, dim, r0, r1, r0, b, rows, a, 0, FLAG_SKIP_LOWER | FLAG_MIRROR)
+                if b < n and self.staging is not None:
+                    engine.distance_block(metric, P, aux, dim, r0, r1, b, n, rows, a, 0, FLAG_MIRROR,
+                                          mirror=self.staging[i], mirror_row0=b, mirror_col0=a)
+                elif b < n:
+                    # one launch per block right of the diagonal; its transposed tiles are stored into the
+                    # rows of the rank that owns that range (local or peer address, row pitch n)
+                    for q in range(i + 1, len(self.ranges)):
+                        aq, bq = self.ranges[q]
+                        if bq <= aq:
+                            continue
+                        owner = sharding.range_owner(q, self.world)
+                        base = self.matrix.data_ptr() if owner == self.rank else self.peers.address(owner)
+                        addr = base + self.offsets[q] * n * self.esize
+                        engine.distance_block(metric, P, aux, dim, r0, r1, aq, bq, rows, a, 0, FLAG_MIRROR,
+                                              mirror=addr, mirror_row0=aq, mirror_col0=0, mirror_ld=n)
+                if ship is not None:
+                    ship_panel(i, r0, r1)
         if self.peers is not None:
             self._device_barrier()
         elif self.world > 1:
             sharding.exchange_transposed(self.staging, self.ranges, self.rank, self.world, self.out_rows)
         if ship is not None and left_parts:
             for i in self.my_ranges:
-                ship_part(i, right=False)
+                ship_left(i)
         if host_rows is not None:
             torch.cuda.current_stream().wait_stream(self._copy_stream)
         return self.matrix

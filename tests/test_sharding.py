@@ -107,8 +107,9 @@ def _block_rows_worker(rank, world, port, n, dim):
                        mirror_row0=0, mirror_col0=0, mirror_ld=None):
             calls.append((row0, row1, col0, col1))
             blk = full[row0:row1, col0:col1]
-            if flags & FLAG_SKIP_LOWER:  # diagonal block: upper triangle computed, mirrored in place
-                assert (row0, row1) == (col0, col1) and mirror is None
+            if flags & FLAG_SKIP_LOWER:  # (a row panel of) the diagonal block: upper triangle computed, mirrored in place
+                assert row0 == col0 and row1 <= col1 and mirror is None and (flags & FLAG_MIRROR)
+                out[col0 - out_row0:col1 - out_row0, row0 - out_col0:row1 - out_col0] = blk.T
             out[row0 - out_row0:row1 - out_row0, col0 - out_col0:col1 - out_col0] = blk
             if (flags & FLAG_MIRROR) and mirror is not None:
                 assert isinstance(mirror, torch.Tensor)  # the NCCL-exchange path stages locally
@@ -170,14 +171,38 @@ def _block_rows_worker(rank, world, port, n, dim):
         engine.distance_block = fake_block
         try:
             job.compute("Eucl", None, None, dim, ship=sink.ship, left_parts=False)
+            sink.finish()
+            dist.barrier()
+            assert torch.equal(host, full.float()), "rank %d: shared host matrix" % rank
+            tri = sum((job.ranges[i][1] - job.ranges[i][0]) * (n - job.ranges[i][0]) for i in job.my_ranges) * 4
+            low = sum((job.ranges[i][1] - job.ranges[i][0]) * (n - job.ranges[i][1]) for i in job.my_ranges) * 4
+            assert sink.dma_bytes == tri and sink.mirrored_bytes == low
+            dist.barrier()
+            # the same with the block rows launched and shipped in row panels: a panel's part right of its own
+            # square is mirrored below it, inside the block row as well
+            if rank == 0:
+                fm.array[:] = np.nan
+            job.matrix.fill_(float("nan"))
+            dist.barrier()
+            sink.reset()
+            job.compute("Eucl", None, None, dim, ship=sink.ship, left_parts=False, panel_rows=128)
+            sink.finish()
+            dist.barrier()
+            assert torch.equal(host, full.float()), "rank %d: shared host matrix, row panels" % rank
+            for i, rows in job.out_rows.items():
+                a, b = job.ranges[i]
+                assert torch.equal(rows, full[a:b]), "rank %d block row %d, row panels" % (rank, i)
+            # the lower halves of the diagonal blocks are mirrored too now: fewer bytes by "DMA", as many more by the host
+            assert sink.dma_bytes <= tri and sink.dma_bytes + sink.mirrored_bytes == tri + low
+            # row panels through the plain callback: right parts panel by panel, left parts at the end, no overlap
+            shipped.fill_(float("nan"))
+            del order[:]
+            job.compute("Eucl", None, None, dim, ship=ship, panel_rows=256)
+            for i in job.my_ranges:
+                a, b = job.ranges[i]
+                assert torch.equal(shipped[a:b], full[a:b]), "rank %d shipped rows of block row %d, row panels" % (rank, i)
         finally:
             engine.distance_block = keep
-        sink.finish()
-        dist.barrier()
-        assert torch.equal(host, full.float()), "rank %d: shared host matrix" % rank
-        tri = sum((job.ranges[i][1] - job.ranges[i][0]) * (n - job.ranges[i][0]) for i in job.my_ranges) * 4
-        low = sum((job.ranges[i][1] - job.ranges[i][0]) * (n - job.ranges[i][1]) for i in job.my_ranges) * 4
-        assert sink.dma_bytes == tri and sink.mirrored_bytes == low
         dist.barrier()
         pool.close()
         del host, sink

@@ -6,7 +6,7 @@ exchange) and compares them bit for bit with the same rows of a single-GPU run o
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
-from phyloligo_b200 import engine, multigpu
+from phyloligo_b200 import engine, hostsink, multigpu
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -28,6 +28,37 @@ for exchange in ("peer", "nccl"):
         torch.cuda.synchronize()
         ok = all(torch.equal(job.out_rows[i], full[job.ranges[i][0]:job.ranges[i][1]]) for i in job.out_rows)
         ok = ok and (job.rows_owned == 0 or torch.equal(host[:job.rows_owned], job.matrix[:job.rows_owned].cpu()))
+        # third pass: block rows launched and shipped in row panels, only the upper triangle crosses PCIe into ONE
+        # matrix in shared memory (own rows page-locked), the rest is mirrored there by the rank that shipped it
+        path = "/dev/shm/po_check_%s_%s_%s.mat" % (os.environ.get("MASTER_PORT", "0"), exchange, metric)
+        if rank == 0:
+            fm = hostsink.FileMatrix(path, n, n, np.float32, create=True)
+            fm.array[:] = np.nan
+        dist.barrier()
+        if rank != 0:
+            fm = hostsink.FileMatrix(path, n, n, np.float32, create=False)
+        registered = fm.register_rows([job.ranges[i] for i in job.my_ranges])
+        shared = torch.from_numpy(fm.array)
+        pool = engine.HostMirror(3)
+        sink = multigpu.MirroredHostSink(shared, pool, sub_rows=128)
+        job.matrix.fill_(float("nan"))
+        torch.cuda.synchronize()
+        dist.barrier()
+        job.compute(metric, P, aux, d, ship=sink.ship, left_parts=False, panel_rows=256)
+        sink.finish()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ok = ok and all(torch.equal(job.out_rows[i], full[job.ranges[i][0]:job.ranges[i][1]]) for i in job.out_rows)
+        ok3 = torch.equal(shared, full.cpu())
+        if not ok3:
+            print("rank %d: shared host matrix differs (%s, %s; rows registered: %s)" % (rank, exchange, metric, registered), flush=True)
+        ok = ok and ok3
+        dist.barrier()
+        pool.close()
+        del shared, sink
+        fm.close()
+        if rank == 0:
+            os.unlink(path)
         flag = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
