@@ -796,6 +796,16 @@ def run_ours(args):
         engine.distance_block("JSD", P, aux, dim, r, r + 1, 0, n_contigs, blk, r, 0)
         return blk[0].cpu().numpy()
 
+    def host_equals_device(host_rows, dev_rows, what):
+        """every entry of the host result against the device result, bit for bit: the host rows go back to the
+        device in chunks (outside the timed region)"""
+        chunk = max(1, (256 << 20) // (n_contigs * 4))
+        buf = torch.empty((chunk, n_contigs), dtype=torch.float32, device=device)
+        for r0 in range(0, int(host_rows.shape[0]), chunk):
+            r1 = min(int(host_rows.shape[0]), r0 + chunk)
+            engine.copy2d(buf[:r1 - r0], host_rows[r0:r1])
+            assert torch.equal(buf[:r1 - r0], dev_rows[r0:r1]), "%s differs from the device result in rows [%d, %d)" % (what, r0, r1)
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -838,6 +848,7 @@ def run_ours(args):
         picks = sorted(set(int(v) for v in np.linspace(0, host_rows_n - 1, 41)))
         for r in picks:
             assert torch.equal(host_result[r], matrix[r].cpu()), "end-to-end host matrix differs from the device matrix in row %d" % r
+        host_equals_device(host_result, matrix[:host_rows_n], "end-to-end host matrix")  # every entry, bit for bit
     if shared_host is not None:  # after timed()'s closing barrier every rank's share is in the shared matrix
         torch.cuda.synchronize()
         for i in job.my_ranges:
@@ -845,6 +856,7 @@ def run_ours(args):
             for r in sorted(set(int(v) for v in np.linspace(a, b - 1, 9))):
                 assert torch.equal(shared_host[1][r], job.out_rows[i][r - a].cpu()), \
                     "end-to-end shared host matrix differs from the device rows in row %d" % r
+            host_equals_device(shared_host[1][a:b], job.out_rows[i], "shared host matrix, rows [%d, %d)" % (a, b))
     io_bytes = torch.tensor([e2e_bytes["h2d"], e2e_bytes["d2h"], e2e_stats.get("host_mirrored_bytes", 0)],
                             dtype=torch.float64, device=device)
     if world > 1:
@@ -959,9 +971,10 @@ def run_ours(args):
                 "flop_convention": "10 flop per dimension per pair (SURVEY.md 8d); D=256",
                 "avg_launch_ms": avg_launch_ms, "launches_timed": int(dist_n),
                 "mufu_lg2_peak_Tops": mufu_peak,
-                "recipe_note": "the kernel spends 12 FP32-pipe operations + 1 MUFU per (pair, dimension) on a "
-                               "cancellation-free series; at 100 % FP32-pipe utilisation that is 10/24 = 0.42 of "
-                               "the 10-flop convention (ncu: sm__pipe_fma_cycles_active 79.0 %, profiles/r01b_jsd_tile_ncu_summary.txt)",
+                "recipe_note": "the kernel spends 10 (chunks whose value ranges prove u <= 1/4) to 12 FP32-pipe operations "
+                               "+ 1 MUFU per (pair, dimension) on a cancellation-free series; at 100 % FP32-pipe utilisation "
+                               "that is 0.50 / 0.42 of the 10-flop convention, 0.465 for this workload's mix of chunk variants "
+                               "(ncu: sm__pipe_fma_cycles_active 80.0 %, profiles/r02b_jsd_tile_full_ncu_summary.txt; DESIGN.md 4.3)",
             },
             "e2e_cli": e2e_cli,
             "stages": {

@@ -19,6 +19,7 @@
 // prefetcher.  Without AVX2 (or with a pitch that breaks the 32-byte alignment) the 4 x 4 SSE form
 // runs instead.
 #include <immintrin.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -81,6 +82,7 @@ __attribute__((target("avx2"))) static inline void transpose8x8(__m256 (&r)[8]) 
 // dst[c][r] = src[r][c] for r in [0, rows), c in [c0, c1).  Requires ldd % 8 == 0 and r_al = the first
 // row whose destination address is 32-byte aligned (the same for every c); rows below r_al and the
 // ragged ends go through the SSE / scalar path.
+template <bool NT>
 __attribute__((target("avx2"))) static void strip_avx2(float* dst, int64_t ldd, const float* src, int64_t lds, int64_t rows,
                                                        int64_t c0, int64_t c1, int64_t r_al) {
     if (r_al > rows) r_al = rows;
@@ -103,19 +105,32 @@ __attribute__((target("avx2"))) static void strip_avx2(float* dst, int64_t ldd, 
                 transpose8x8(y);
                 for (int k = 0; k < 8; ++k) {
                     float* d = dst + (c + k) * ldd + r;
-                    _mm256_stream_ps(d, x[k]);
-                    _mm256_stream_ps(d + 8, y[k]);
+                    if (NT) {
+                        _mm256_stream_ps(d, x[k]);
+                        _mm256_stream_ps(d + 8, y[k]);
+                    } else {
+                        _mm256_store_ps(d, x[k]);
+                        _mm256_store_ps(d + 8, y[k]);
+                    }
                 }
             }
         }
     }
-    _mm_sfence();
+    if (NT) _mm_sfence();
     if (full < rows) strip_sse(dst + full, ldd, src + full * lds, lds, rows - full, c0, c8);
     if (c8 < c1) strip_sse(dst + r_al, ldd, src + r_al * lds, lds, rows - r_al, c8, c1);
 }
 
 static bool have_avx2() {
     static const bool v = __builtin_cpu_supports("avx2");
+    return v;
+}
+// PO_HOST_MIRROR_NT=0: ordinary stores instead of streaming stores (a tuning switch)
+static bool use_nt_stores() {
+    static const bool v = [] {
+        const char* e = getenv("PO_HOST_MIRROR_NT");
+        return !(e && e[0] == '0');
+    }();
     return v;
 }
 
@@ -127,7 +142,8 @@ static void transpose_strip(float* dst, int64_t ldd, const float* src, int64_t l
         const uintptr_t a = (uintptr_t)(dst + c0 * ldd);
         const uintptr_t m = (ldd % 16 == 0) ? 63 : 31;
         const int64_t r_al = (int64_t)(((m + 1 - (a & m)) & m) / 4);
-        strip_avx2(dst, ldd, src, lds, rows, c0, c1, r_al);
+        if (use_nt_stores()) strip_avx2<true>(dst, ldd, src, lds, rows, c0, c1, r_al);
+        else strip_avx2<false>(dst, ldd, src, lds, rows, c0, c1, r_al);
     } else {
         strip_sse(dst, ldd, src, lds, rows, c0, c1);
     }
