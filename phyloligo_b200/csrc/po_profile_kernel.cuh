@@ -5,7 +5,8 @@
 //
 // Layout / algorithm
 //   * the raw FASTA text sits in HBM once; a record is a byte range whose
-//     '\n', '\r', ' ' bytes are transparent (Biopython strips them).
+//     '\n', '\r', ' ' and the other ASCII blanks (TAB, VT, FF) are transparent: Biopython drops blanks and CR
+//     anywhere and strips every kind of trailing white space from a line.
 //   * one CTA per record.  Each thread walks 64-byte, 16-byte-aligned chunks with
 //     128-bit coalesced loads.  Every byte is classified through a 256-entry table in
 //     shared memory (2-bit code, "not ACGT" flag, "skip" flag; C=0,G=1,A=2,T=3 so the
@@ -41,7 +42,7 @@ constexpr int CHUNK = 64;  // bytes per thread step
 
 // class byte: bits 0-1 code, bit 2 invalid (not ACGT after upper-casing), bit 3 skip
 __device__ __forceinline__ uint32_t classify_byte(uint32_t c) {
-    if (c == 10u || c == 13u || c == 32u) return 8u;
+    if (c == 32u || (c >= 9u && c <= 13u)) return 8u;  // space, TAB, LF, VT, FF, CR
     const uint32_t up = c & 0xDFu;
     if (up == 0x43u) return 0u;  // C
     if (up == 0x47u) return 1u;  // G

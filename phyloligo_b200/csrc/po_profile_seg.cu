@@ -90,7 +90,7 @@ __device__ __forceinline__ void sg_bulk_g2s(unsigned dst, const void* src, unsig
 
 // class byte of the per-byte path: bits 0-1 internal code, bit 2 invalid, bit 3 skip
 __device__ __forceinline__ uint32_t seg_classify(uint32_t c) {
-    if (c == 10u || c == 13u || c == 32u) return 8u;
+    if (c == 32u || (c >= 9u && c <= 13u)) return 8u;  // space, TAB, LF, VT, FF, CR: transparent
     const uint32_t up = c & 0xDFu;
     if (up == 0x41u) return 0u;  // A
     if (up == 0x43u) return 1u;  // C

@@ -62,7 +62,7 @@ class Assembly:
             fields = header[1:].split()
             self.ids.append(fields[0].decode("latin-1") if fields else "")
             seg = text[int(begin[i]):int(end[i])]
-            seq = seg[(seg != 10) & (seg != 13) & (seg != 32)]
+            seq = seg[(seg != 32) & ((seg < 9) | (seg > 13))]  # blanks are transparent, as in the profiling kernels
             offsets[i], lengths[i] = pos, seq.shape[0]
             parts.append(seq)
             parts.append(sep)

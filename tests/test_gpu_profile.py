@@ -101,7 +101,8 @@ def _layout(seqs, rng, widths, crlf=False, blank_lines=False, trailing_space=Fal
             line = s[p:p + w]
             p += w
             if trailing_space and rng.random() < 0.2:
-                line += b" "
+                # what Biopython's line.rstrip() drops: blanks of every kind, also several of them
+                line += [b" ", b"\t", b"\x0b", b"\x0c", b" \t ", b"\t\t"][int(rng.integers(0, 6))]
             parts.append(line + (b"\r\n" if crlf else b"\n"))
             if blank_lines and rng.random() < 0.1:
                 parts.append(b"\n")

@@ -195,7 +195,7 @@ def test_kount_assembly_layout_matches_the_fasta_reader(tmp_path):
 
     path = os.path.join(tmp_path, "a.fasta")
     with open(path, "wb") as fh:
-        fh.write(b"junk before the first record\n>c1 first contig\nACGT\nacgtNN\n\n>c2\n>c3|x desc\r\nAC GT\r\nTT\r\n>last\nGATTACA")
+        fh.write(b"junk before the first record\n>c1 first contig\nACGT\nacgtNN\n\n>c2\n>c3|x desc\r\nAC GT\t\r\nTT \x0b\r\n>last\nGATTACA")
     asm = kount.Assembly(path)
     want = ko.read_records(path)
     assert asm.ids == [w[0] for w in want] == ["c1", "c2", "c3|x", "last"]
@@ -239,7 +239,7 @@ def test_fasta_index_fuzz_against_the_reader(tmp_path):
     from hypothesis import given, settings, strategies as st
 
     line = st.one_of(
-        st.text(alphabet="ACGTNacgtn >", min_size=0, max_size=30),
+        st.text(alphabet="ACGTNacgtn >\t\x0c", min_size=0, max_size=30),
         st.text(alphabet="ACGT", min_size=0, max_size=5).map(lambda s: ">" + s + " desc"),
         st.just(""), st.just(">"), st.just(">>x"))
     path = os.path.join(tmp_path, "fuzz.fa")
@@ -253,7 +253,8 @@ def test_fasta_index_fuzz_against_the_reader(tmp_path):
             fh.write(raw)
         want = list(po.read_fasta(path))
         begin, end = engine.fasta_index(raw, threads=2)
-        got = [bytes(raw[b:e]).decode().replace("\n", "").replace("\r", "").replace(" ", "") for b, e in zip(begin, end)]
+        got = [bytes(raw[b:e]).decode().replace("\n", "").replace("\r", "").replace(" ", "").replace("\t", "").replace("\x0c", "")
+               for b, e in zip(begin, end)]
         assert got == want
 
     run()
