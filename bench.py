@@ -452,7 +452,8 @@ def run_select_leg(matrix, hbm_peak):
                      "cluster_sizes": np.bincount(km.labels_, minlength=2).tolist(),
                      "passes_over_the_matrix": 1 + int(km.n_iter_), "note": "heuristic initialisation + one masked pass per iteration"},
         "knn": {"k": k, "ms": ms_knn, "gbytes_per_s_one_pass_equivalent": nbytes / (ms_knn * 1e-3) / 1e9,
-                "note": "radix select: four histogram passes + one gather pass over every row"},
+                "note": "one pass over every row: threshold from an 8192-entry sample of the row, candidates below it sorted in "
+                        "shared memory; the exact radix select (four histogram passes + a gather) is the fallback"},
     }
 
 

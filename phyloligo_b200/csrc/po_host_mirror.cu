@@ -286,7 +286,16 @@ int po_host_mirror_submit(void* h_pool, po_stream_t stream, int after_stream, fl
         set_error("po_host_mirror_submit: NULL pointer");
         return PO_ERR_ARG;
     }
-    auto job = std::make_shared<MirrorJob>();
+    // nothing below may throw across the C boundary
+    std::shared_ptr<MirrorJob> job;
+    MirrorTicket* ticket = nullptr;
+    try {
+        job = std::make_shared<MirrorJob>();
+        if (after_stream) ticket = new MirrorTicket{pool, job};
+    } catch (...) {
+        set_error("po_host_mirror_submit: out of memory");
+        return PO_ERR_ARG;
+    }
     job->dst = h_dst;
     job->ldd = ld_dst;
     job->src = h_src;
@@ -302,7 +311,6 @@ int po_host_mirror_submit(void* h_pool, po_stream_t stream, int after_stream, fl
         pool->release(std::move(job));
         return PO_OK;
     }
-    MirrorTicket* ticket = new MirrorTicket{pool, std::move(job)};
     const cudaError_t e = cudaLaunchHostFunc(static_cast<cudaStream_t>(stream), mirror_release_cb, ticket);
     if (e != cudaSuccess) {
         delete ticket;
