@@ -149,13 +149,27 @@ static void transpose_strip(float* dst, int64_t ldd, const float* src, int64_t l
     }
 }
 
+// A block is cut into pieces of (at most job_rows source rows) x (64 source columns), walked row block by
+// row block: the threads of the pool work inside one row block at a time.  Short row blocks matter -- with
+// whole 4096-row panels as one piece per strip the pool's strided reads (one 256-byte run out of every
+// 400 KB row) slowed the DMA that runs beside them from 52 to 39 GB/s, with 256-row blocks to 50 GB/s
+// (profiles/r02e_sink_job_rows_probe.log).
 struct MirrorJob {
     float* dst;
     int64_t ldd;
     const float* src;
-    int64_t lds, rows, cols, nstrips;
+    int64_t lds, rows, cols, job_rows, cstrips, nstrips;
     std::atomic<int64_t> next{0}, done{0};
 };
+
+static int64_t mirror_job_rows() {
+    static const int64_t v = [] {
+        const char* e = getenv("PO_HOST_MIRROR_JOB_ROWS");
+        const long long r = e ? atoll(e) : 0;
+        return (int64_t)(r >= 16 ? r : 256);
+    }();
+    return v;
+}
 
 struct MirrorPool {
     std::mutex mu;
@@ -184,8 +198,10 @@ struct MirrorPool {
             for (;;) {
                 const int64_t s = j->next.fetch_add(1, std::memory_order_relaxed);
                 if (s >= j->nstrips) break;
-                const int64_t c0 = s * MT, c1 = std::min(j->cols, c0 + MT);
-                transpose_strip(j->dst, j->ldd, j->src, j->lds, j->rows, c0, c1);
+                const int64_t rb = s / j->cstrips, cs = s - rb * j->cstrips;
+                const int64_t r0 = rb * j->job_rows, nr = std::min(j->job_rows, j->rows - r0);
+                const int64_t c0 = cs * MT, c1 = std::min(j->cols, c0 + MT);
+                transpose_strip(j->dst + r0, j->ldd, j->src + r0 * j->lds, j->lds, nr, c0, c1);
                 if (j->done.fetch_add(1, std::memory_order_acq_rel) + 1 == j->nstrips) {
                     {
                         std::lock_guard<std::mutex> lk(mu);
@@ -302,7 +318,9 @@ int po_host_mirror_submit(void* h_pool, po_stream_t stream, int after_stream, fl
     job->lds = ld_src;
     job->rows = rows;
     job->cols = cols;
-    job->nstrips = (cols + MT - 1) / MT;
+    job->job_rows = mirror_job_rows();
+    job->cstrips = (cols + MT - 1) / MT;
+    job->nstrips = job->cstrips * ((rows + job->job_rows - 1) / job->job_rows);
     {
         std::lock_guard<std::mutex> lk(pool->mu);
         ++pool->submitted;

@@ -519,6 +519,8 @@ def default_host_mirror_share():
 
 # Measured on the B200 hosts of this pool (16 cores, PCIe 52 GB/s, tools/e2e_mirror_sweep.py): see DESIGN.md 6.1
 HOST_MIRROR_DEFAULT = 1.0
+# rows per strided DMA of a panel's right part (tools/shared_sink_probe.py, profiles/r02e_sink_job_rows_probe.log)
+DMA_ROWS = 256
 
 
 def matrix_to_host(X, metric, host, out_dtype=torch.float32, panel_rows=4096, prepared=None, device_matrix=None,
@@ -564,7 +566,10 @@ def matrix_to_host(X, metric, host, out_dtype=torch.float32, panel_rows=4096, pr
         ready = torch.cuda.Event()
         ready.record(compute)
         copy_stream.wait_event(ready)
-        copy2d(host[r0:r1, r0:], full[r0:r1, r0:], copy_stream)
+        # in DMA_ROWS-row pieces: beside the host's mirroring short copies keep a little more of the link's rate
+        for d0 in range(r0, r1, DMA_ROWS):
+            d1 = min(r1, d0 + DMA_ROWS)
+            copy2d(host[d0:d1, r0:], full[d0:d1, r0:], copy_stream)
         # rows [r1, rs) of the mirrored column block by DMA, rows [rs, n) by the host from host[r0:r1, rs:]
         rs = n - int(round(share * (n - r1))) if pool is not None else n
         if rs < n:

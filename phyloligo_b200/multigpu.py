@@ -198,21 +198,23 @@ class MirroredHostSink:
     `host` is the whole n x n float32 matrix in host memory that every rank of the node maps (a file
     under /dev/shm: ``hostsink.FileMatrix``; a rank's own rows page-locked so that DMA lands in them).
     ``ship`` (the callback of ``BlockRows.compute(..., ship=sink.ship, left_parts=False)``) takes the
-    part of a block row from its diagonal block rightwards, sends it to the rank's rows of `host` in
-    sub-panels of `sub_rows` rows by strided DMA, and queues behind every sub-panel the transposition
-    of its columns right of the diagonal block into the rows below (``engine.HostMirror``, released in
+    part of a block row (or of a row panel of it) from its diagonal square rightwards, sends it to the rank's
+    rows of `host` by strided DMA, and queues behind it (or behind every `sub_rows` rows of it) the transposition
+    of its columns right of that square into the rows below (``engine.HostMirror``, released in
     stream order) -- rows that other ranks own.  Every entry left of the diagonal is therefore written
     by the rank that computed its mirror image, from host memory, and no rank ships the left part of
     its rows: half of the bytes cross PCIe.  The regions the ranks write are disjoint; the matrix is
     complete when every rank has called ``finish`` (a barrier is the caller's).  The reference's
     workers assign whole block rows (output[s] = ..., bin/phyloligo.py:202-222)."""
 
-    def __init__(self, host, pool, sub_rows=1024):
+    def __init__(self, host, pool, sub_rows=None):
         if host.dim() != 2 or host.shape[0] != host.shape[1] or host.dtype != torch.float32 or host.is_cuda:
             raise RuntimeError("MirroredHostSink: host must be a square float32 host tensor")
         self.host, self.pool = host, pool
         self.n = int(host.shape[0])
-        self.sub = max(1, int(sub_rows))
+        # rows per mirror submit = per stream callback (None: a whole shipped block; a callback stalls the copy
+        # stream for ~0.2 ms, profiles/r02e_sink_callback_granularity_probe.log)
+        self.sub = max(1, int(sub_rows)) if sub_rows else None
         self._copy_stream = None
         self.reset()
 
@@ -233,11 +235,14 @@ class MirroredHostSink:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream())
             self._copy_stream.wait_event(ready)
-        for r0 in range(0, h, self.sub):
-            r1 = min(h, r0 + self.sub)
+        sub = self.sub or h
+        for r0 in range(0, h, sub):
+            r1 = min(h, r0 + sub)
             dst = self.host[row0 + r0:row0 + r1, col0:]
             if on_device:
-                engine.copy2d(dst, block[r0:r1], self._copy_stream)
+                for d0 in range(r0, r1, engine.DMA_ROWS):
+                    d1 = min(r1, d0 + engine.DMA_ROWS)
+                    engine.copy2d(self.host[row0 + d0:row0 + d1, col0:], block[d0:d1], self._copy_stream)
             else:  # the CPU stand-in of the gloo tests
                 dst.copy_(block[r0:r1])
             self.dma_bytes += (r1 - r0) * (self.n - col0) * 4

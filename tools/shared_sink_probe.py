@@ -20,6 +20,7 @@ ap.add_argument("--panel", type=int, default=4096)
 ap.add_argument("--sub", type=int, default=1024)
 ap.add_argument("--threads", default="4,8,14")
 ap.add_argument("--only-pinned", action="store_true")
+ap.add_argument("--dma-rows", type=int, default=0)
 args = ap.parse_args()
 n, panel, sub = args.n, args.panel, args.sub
 dev = torch.device("cuda", 0)
@@ -29,6 +30,7 @@ matrix = torch.empty((n, n), dtype=torch.float32, device=dev)
 matrix.copy_(torch.rand((1, n), device=dev).expand(n, n))
 matrix += torch.arange(n, device=dev, dtype=torch.float32)[:, None]
 torch.cuda.synchronize()
+print("PO_HOST_MIRROR_JOB_ROWS=%s dma-rows=%d" % (os.environ.get("PO_HOST_MIRROR_JOB_ROWS", "(default)"), args.dma_rows))
 print("n = %d: %.1f GB; cpus %d; THP anon: %s; shmem: %s" % (
     n, n * n * 4 / 1e9, os.cpu_count(),
     open("/sys/kernel/mm/transparent_hugepage/enabled").read().strip(),
@@ -41,7 +43,8 @@ def panels():
 
 
 def run(host, pool, do_dma, do_mirror, sub_rows):
-    """one pass; returns seconds"""
+    """one pass; returns seconds.  sub_rows = rows per mirror submit (one stream callback each);
+    --dma-rows = rows per strided DMA (0: the same)"""
     cs = torch.cuda.Stream()
     torch.cuda.synchronize()
     t = time.perf_counter()
@@ -49,7 +52,10 @@ def run(host, pool, do_dma, do_mirror, sub_rows):
         for s0 in range(r0, r1, sub_rows):
             s1 = min(r1, s0 + sub_rows)
             if do_dma:
-                engine.copy2d(host[s0:s1, r0:], matrix[s0:s1, r0:], cs)
+                step = args.dma_rows or (s1 - s0)
+                for d0 in range(s0, s1, step):
+                    d1 = min(s1, d0 + step)
+                    engine.copy2d(host[d0:d1, r0:], matrix[d0:d1, r0:], cs)
             if do_mirror and r1 < n:
                 pool.submit(host[r1:, s0:s1], host[s0:s1, r1:], cs, after_stream=do_dma)
     cs.synchronize()
