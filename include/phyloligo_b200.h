@@ -271,6 +271,10 @@ int po_savetxt_host(const char* path, const void* h_data, int64_t rows, int64_t 
  * `threads` <= 0 picks the hardware concurrency.
  *   po_host_prefault      instantiate the pages of [h_ptr, h_ptr + bytes) for writing (parallel
  *                         madvise(MADV_POPULATE_WRITE); touches every page on kernels without it)
+ *   po_host_premap        map the pages of a shared mapping of an EXISTING file (descriptor fd) ahead of the
+ *                         writes: on tmpfs by populating for reading (fault-around maps 16 up-to-date pages per
+ *                         fault and the entries are writable at once: 27-43 GB/s against 2-3 GB/s per thread),
+ *                         elsewhere like po_host_prefault
  *   po_host_register      page-lock an existing mapping (cudaHostRegister, portable) so that
  *                         po_copy2d_async DMAs straight into it; fails with PO_ERR_CUDA when the
  *                         kernel refuses to pin the pages (file systems with dirty tracking)
@@ -295,6 +299,7 @@ int po_savetxt_host(const char* path, const void* h_data, int64_t rows, int64_t 
  *                         without crossing PCIe.
  */
 int po_host_prefault(void* h_ptr, int64_t bytes, int threads);
+int po_host_premap(int fd, void* h_ptr, int64_t bytes, int threads);
 int po_host_register(void* h_ptr, int64_t bytes);
 int po_host_unregister(void* h_ptr);
 int po_host_copy2d(void* h_dst, int64_t dst_pitch, const void* h_src, int64_t src_pitch, int64_t width,

@@ -27,7 +27,7 @@ EXPORTED = [
     "po_version", "po_last_error", "po_device_info", "po_pattern_info", "po_fasta_index_host",
     "po_profile_batch", "po_prepared_row_bytes", "po_prepared_bytes", "po_prepare_profiles", "po_rank_transform", "po_distance_block", "po_distance_block_ex",
     "po_ipc_export", "po_ipc_open", "po_ipc_close", "po_savetxt_host", "po_copy2d_async", "po_window_count_byte", "po_window_distances",
-    "po_host_prefault", "po_host_register", "po_host_unregister", "po_host_copy2d", "po_host_pwrite2d",
+    "po_host_prefault", "po_host_premap", "po_host_register", "po_host_unregister", "po_host_copy2d", "po_host_pwrite2d",
     "po_host_pread", "po_host_transpose_f32",
     "po_host_mirror_open", "po_host_mirror_submit", "po_host_mirror_wait", "po_host_mirror_close",
     "po_matrix_rowsums", "po_matrix_argmin_rows", "po_cluster_argmin", "po_matrix_knn", "po_launch_count", "po_timing_enable", "po_timing_reset", "po_timing_read", "po_microbench",
@@ -94,6 +94,8 @@ def load():
     lib.po_savetxt_host.restype = i32
     lib.po_host_prefault.argtypes = [vp, i64, i32]
     lib.po_host_prefault.restype = i32
+    lib.po_host_premap.argtypes = [i32, vp, i64, i32]
+    lib.po_host_premap.restype = i32
     lib.po_host_register.argtypes = [vp, i64]
     lib.po_host_register.restype = i32
     lib.po_host_unregister.argtypes = [vp]

@@ -15,6 +15,7 @@
 #include <fcntl.h>
 #include <string.h>
 #include <sys/mman.h>
+#include <sys/vfs.h>
 #include <unistd.h>
 #include <algorithm>
 #include <atomic>
@@ -26,14 +27,19 @@
 #ifndef MADV_POPULATE_WRITE
 #define MADV_POPULATE_WRITE 23
 #endif
+#ifndef MADV_POPULATE_READ
+#define MADV_POPULATE_READ 22
+#endif
 
 using namespace po;
 
 extern "C" {
 
-int po_host_prefault(void* h_ptr, int64_t bytes, int threads) {
+// madvise(advice) over [h_ptr, h_ptr + bytes) on `threads` threads, 64 MB per call; falls back to touching
+// every page (read or read-modify-write) on kernels without MADV_POPULATE_* (before 5.14)
+static int populate_range(const char* who, void* h_ptr, int64_t bytes, int threads, int advice) {
     if (bytes < 0 || (bytes > 0 && !h_ptr)) {
-        set_error("po_host_prefault: bad arguments");
+        set_error("%s: bad arguments", who);
         return PO_ERR_ARG;
     }
     if (bytes == 0) return PO_OK;
@@ -51,7 +57,7 @@ int po_host_prefault(void* h_ptr, int64_t bytes, int threads) {
         bool use_madvise = true;
         while (a < b) {
             const uintptr_t e = std::min(b, a + step);
-            if (use_madvise && madvise((void*)a, e - a, MADV_POPULATE_WRITE) != 0) {
+            if (use_madvise && madvise((void*)a, e - a, advice) != 0) {
                 if (errno == EINVAL || errno == ENOSYS) {
                     use_madvise = false;  // kernel older than 5.14: touch every page instead
                 } else {
@@ -62,17 +68,33 @@ int po_host_prefault(void* h_ptr, int64_t bytes, int threads) {
             if (!use_madvise) {
                 for (uintptr_t q = a; q < e; q += page) {
                     volatile unsigned char* c = (volatile unsigned char*)q;
-                    *c = *c;
+                    if (advice == MADV_POPULATE_WRITE) *c = *c;
+                    else (void)*c;
                 }
             }
             a = e;
         }
     });
     if (failed.load()) {
-        set_error("po_host_prefault: madvise(MADV_POPULATE_WRITE) failed: %s", strerror(failed.load()));
+        set_error("%s: madvise failed: %s", who, strerror(failed.load()));
         return PO_ERR_ARG;
     }
     return PO_OK;
+}
+
+int po_host_prefault(void* h_ptr, int64_t bytes, int threads) {
+    return populate_range("po_host_prefault", h_ptr, bytes, threads, MADV_POPULATE_WRITE);
+}
+
+int po_host_premap(int fd, void* h_ptr, int64_t bytes, int threads) {
+    // A shared mapping of a tmpfs file needs no write notification: its page-table entries are writable from
+    // the first (read) fault on, and a read fault maps the 16 pages around it in one go (fault-around) when
+    // they exist and are up to date.  Populating for reading therefore maps an EXISTING file ten times
+    // faster than populating for writing (one fault per page), and later writes fault no more.  On other file
+    // systems (dirty tracking: entries would come up read-only) populate for writing as before.
+    struct statfs sfs;
+    const bool tmpfs = fd >= 0 && fstatfs(fd, &sfs) == 0 && (unsigned long)sfs.f_type == 0x01021994ul;  // TMPFS_MAGIC
+    return populate_range("po_host_premap", h_ptr, bytes, threads, tmpfs ? MADV_POPULATE_READ : MADV_POPULATE_WRITE);
 }
 
 int po_host_register(void* h_ptr, int64_t bytes) {

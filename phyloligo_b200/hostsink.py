@@ -65,6 +65,8 @@ class PageWarmer(threading.Thread):
                             self.mode = "populate"  # file system without fallocate
                     if self.mode in ("fallocate", "populate"):
                         lib.po_host_prefault(C.c_void_p(self.base + a), b - a, self.threads)
+                    elif self.mode == "premap":
+                        lib.po_host_premap(self.fd, C.c_void_p(self.base + a), b - a, self.threads)
         except Exception as exc:  # a warmer must never take the run down: the copies fault the pages in themselves
             self.error = exc
 
@@ -115,8 +117,11 @@ class FileMatrix:
         """Start instantiating the pages of the given row ranges (in that order) in the background.
         A fresh file: fallocate only (allocation runs at 14 GB/s on one thread; mapping the pages is left to
         the copies -- populating them as well contends for the same locks and measured slower, 4.7 against
-        6.6 GB/s for the whole chain).  A file whose pages exist: populate (map them ahead of the copies:
-        12.7 against 9 GB/s).  PO_SINK_WARM = none | populate | fallocate | fallocate_only overrides."""
+        6.6 GB/s for the whole chain).  A file whose pages exist: premap -- on tmpfs populate for READING, which
+        maps 16 up-to-date pages per fault with writable entries (27-43 GB/s per the probe against 2-3 GB/s per
+        thread for write-populating, the "populate" mode of the first half of the round: 12.7 against 9 GB/s
+        for the whole chain); other file systems: populate for writing.
+        PO_SINK_WARM = none | premap | populate | fallocate | fallocate_only overrides."""
         if self.mm is None or os.environ.get("PO_SINK_WARM", "") == "none":
             return
         fresh = self.fresh if fresh is None else fresh
@@ -127,7 +132,7 @@ class FileMatrix:
             ranges.append((lo // page * page, min(self.offset + self.nbytes, -(-hi // page) * page)))
         threads = int(os.environ.get("PO_SINK_WARM_THREADS", "0")) or threads
         self.warmer = PageWarmer(self.fd, self.base, ranges, threads,
-                                 mode=os.environ.get("PO_SINK_WARM") or ("fallocate_only" if fresh else "populate"))
+                                 mode=os.environ.get("PO_SINK_WARM") or ("fallocate_only" if fresh else "premap"))
         self.warmer.start()
 
     def register(self):

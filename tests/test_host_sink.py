@@ -110,6 +110,34 @@ def test_mirror_pool_builds_lower_triangle(lib):
     assert lib.po_host_mirror_close(None) == 0
 
 
+@pytest.mark.parametrize("where", ["tmp", "shm"])
+def test_premap_existing_file(lib, tmp_path, where):
+    """po_host_premap maps the pages of an existing file ahead of the writes (tmpfs: populate for reading, the
+    entries are writable at once; elsewhere: populate for writing); what is written afterwards reaches the file."""
+    folder = str(tmp_path) if where == "tmp" else "/dev/shm"
+    if not os.path.isdir(folder):
+        pytest.skip("no " + folder)
+    path = os.path.join(folder, "po_premap_%d.mat" % os.getpid())
+    try:
+        with hostsink.FileMatrix(path, 257, 300, np.float32, create=True) as fm:
+            fm.array[:] = 1.0  # the pages exist and are up to date
+        with hostsink.FileMatrix(path, 257, 300, np.float32, create=False) as fm:
+            assert not fm.fresh
+            assert lib.po_host_premap(fm.fd, fm.array.ctypes.data, fm.nbytes, 3) == 0
+            fm.array[5] = 7.0
+            fm.warm([(0, 257)], threads=2)  # the warmer's mode for an existing file
+            fm.warmer.join()
+            assert fm.warmer.error is None and fm.warmer.mode == "premap"
+            fm.array[200, 299] = -3.0
+        m = np.fromfile(path, np.float32).reshape(257, 300)
+        assert (m[5] == 7.0).all() and m[200, 299] == -3.0 and m[0, 0] == 1.0 and m.sum() == 257 * 300 + 300 * 6 - 4
+        assert lib.po_host_premap(-1, None, 0, 1) == 0
+        assert lib.po_host_premap(-1, None, 8, 1) < 0
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
+
+
 def test_file_matrix_create_attach_warm(tmp_path):
     path = os.path.join(tmp_path, "d.mat")
     with hostsink.FileMatrix(path, 300, 300, np.float32, create=True) as fm:

@@ -23,7 +23,10 @@ nbytes = args.n * args.n * 4
 print("n %d, output %.1f GB under %s" % (args.n, nbytes / 1e9, args.dir), flush=True)
 for setting in args.settings.split(","):
     warm, wt, ct, slot = setting.split(":")
-    os.environ["PO_SINK_WARM"] = warm
+    if warm == "default":  # fresh file: fallocate only; existing file: premap
+        os.environ.pop("PO_SINK_WARM", None)
+    else:
+        os.environ["PO_SINK_WARM"] = warm
     os.environ["PO_SINK_WARM_THREADS"] = wt
     os.environ["PO_SINK_COPY_THREADS"] = ct
     os.environ["PO_SINK_SLOT_MB"] = slot
