@@ -144,12 +144,9 @@ class FileMatrix:
             self.registered = True
         return self.registered
 
-    def register_rows(self, row_ranges):
-        """Page-lock the pages that hold the given row ranges only (a rank's own rows of a matrix every rank
-        maps): adjacent or overlapping ranges are merged, every range is widened to page boundaries.
-        False when the kernel refuses (nothing stays registered then)."""
-        if self.mm is None:
-            return False
+    def page_spans(self, row_ranges):
+        """The byte ranges [lo, hi) of the file that hold the given row ranges, widened to page boundaries,
+        sorted, adjacent or overlapping ones merged (two neighbouring block rows share a page)."""
         page = mmap.PAGESIZE
         spans = []
         for r0, r1 in sorted((int(a), int(b)) for a, b in row_ranges if b > a):
@@ -159,6 +156,15 @@ class FileMatrix:
                 spans[-1][1] = max(spans[-1][1], hi)
             else:
                 spans.append([lo, hi])
+        return spans
+
+    def register_rows(self, row_ranges):
+        """Page-lock the pages that hold the given row ranges only (a rank's own rows of a matrix every rank
+        maps): adjacent or overlapping ranges are merged, every range is widened to page boundaries.
+        False when the kernel refuses (nothing stays registered then)."""
+        if self.mm is None:
+            return False
+        spans = self.page_spans(row_ranges)
         lib = _lib.load()
         done = []
         for lo, hi in spans:

@@ -138,6 +138,23 @@ def test_premap_existing_file(lib, tmp_path, where):
             os.unlink(path)
 
 
+def test_file_matrix_page_spans_merge_neighbours(tmp_path):
+    """FileMatrix.page_spans (what register_rows page-locks): page-aligned, inside the file, neighbours merged."""
+    path = os.path.join(tmp_path, "s.mat")
+    with hostsink.FileMatrix(path, 1000, 1000, np.float32, create=True) as fm:  # 4000-byte rows, 4096-byte pages
+        spans = fm.page_spans([(640, 896), (128, 384), (384, 512), (0, 0)])
+        # rows [128, 512) and [640, 896) are 512 000 bytes apart: two spans; [128, 384) + [384, 512) merge
+        assert len(spans) == 2 and spans[0][0] == 512000 // 4096 * 4096 and spans[0][1] == -(-2048000 // 4096) * 4096
+        assert spans[1] == [2560000 // 4096 * 4096, -(-3584000 // 4096) * 4096]
+        for lo, hi in spans:
+            assert lo % 4096 == 0 and (hi % 4096 == 0 or hi == fm.nbytes) and 0 <= lo < hi <= fm.nbytes
+        assert fm.page_spans([(990, 1000)])[0][1] == fm.nbytes  # clipped to the end of the matrix
+        # two block rows that meet inside one page become one span
+        assert len(fm.page_spans([(0, 5), (5, 9)])) == 1
+    with hostsink.FileMatrix(path, 10, 10, np.float32, offset=4096, create=True) as fm:  # a region at an offset (HDF5)
+        assert fm.page_spans([(0, 10)]) == [[4096, 4096 + 400]]
+
+
 def test_file_matrix_create_attach_warm(tmp_path):
     path = os.path.join(tmp_path, "d.mat")
     with hostsink.FileMatrix(path, 300, 300, np.float32, create=True) as fm:
