@@ -560,27 +560,30 @@ def matrix_to_host(X, metric, host, out_dtype=torch.float32, panel_rows=4096, pr
     copy_stream = torch.cuda.Stream()
     copied = 0
     mirrored = 0
-    for r0 in range(0, n, step):
-        r1 = min(n, r0 + step)
-        distance_block(metric, P, aux, dim, r0, r1, 0, n, full, 0, 0, FLAG_SKIP_LOWER | FLAG_MIRROR)
-        ready = torch.cuda.Event()
-        ready.record(compute)
-        copy_stream.wait_event(ready)
-        # in DMA_ROWS-row pieces: beside the host's mirroring short copies keep a little more of the link's rate
-        for d0 in range(r0, r1, DMA_ROWS):
-            d1 = min(r1, d0 + DMA_ROWS)
-            copy2d(host[d0:d1, r0:], full[d0:d1, r0:], copy_stream)
-        # rows [r1, rs) of the mirrored column block by DMA, rows [rs, n) by the host from host[r0:r1, rs:]
-        rs = n - int(round(share * (n - r1))) if pool is not None else n
-        if rs < n:
-            pool.submit(host[rs:, r0:r1], host[r0:r1, rs:], copy_stream)
-            mirrored += (n - rs) * (r1 - r0) * full.element_size()
-        copy2d(host[r1:rs, r0:r1], full[r1:rs, r0:r1], copy_stream)
-        copied += ((r1 - r0) * (n - r0) + (rs - r1) * (r1 - r0)) * full.element_size()
-    compute.wait_stream(copy_stream)
-    full.record_stream(copy_stream)
-    if pool is not None:
-        pool.wait()
+    try:
+        for r0 in range(0, n, step):
+            r1 = min(n, r0 + step)
+            distance_block(metric, P, aux, dim, r0, r1, 0, n, full, 0, 0, FLAG_SKIP_LOWER | FLAG_MIRROR)
+            ready = torch.cuda.Event()
+            ready.record(compute)
+            copy_stream.wait_event(ready)
+            # in DMA_ROWS-row pieces: beside the host's mirroring short copies keep a little more of the link's rate
+            for d0 in range(r0, r1, DMA_ROWS):
+                d1 = min(r1, d0 + DMA_ROWS)
+                copy2d(host[d0:d1, r0:], full[d0:d1, r0:], copy_stream)
+            # rows [r1, rs) of the mirrored column block by DMA, rows [rs, n) by the host from host[r0:r1, rs:]
+            rs = n - int(round(share * (n - r1))) if pool is not None else n
+            if rs < n:
+                pool.submit(host[rs:, r0:r1], host[r0:r1, rs:], copy_stream)
+                mirrored += (n - rs) * (r1 - r0) * full.element_size()
+            copy2d(host[r1:rs, r0:r1], full[r1:rs, r0:r1], copy_stream)
+            copied += ((r1 - r0) * (n - r0) + (rs - r1) * (r1 - r0)) * full.element_size()
+        compute.wait_stream(copy_stream)
+        full.record_stream(copy_stream)
+    finally:
+        # also on an error: the pool must not be left writing into `host` behind the caller's back
+        if pool is not None and mirrored:
+            pool.wait()
     if stats is not None:
         stats.update(dma_bytes=copied, host_mirrored_bytes=mirrored, mirror_threads=pool.threads if pool else 0)
     return copied
