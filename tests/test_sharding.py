@@ -214,6 +214,6 @@ def _block_rows_worker(rank, world, port, n, dim):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 700), (3, 1000)])
+@pytest.mark.parametrize("world,n", [(2, 700), (3, 1000), (4, 2100)])
 def test_block_rows_orchestration_gloo(world, n):
     mp.spawn(_block_rows_worker, args=(world, _free_port(), n, 12), nprocs=world, join=True)
