@@ -139,7 +139,9 @@ int64_t po_fasta_index_host(const uint8_t* h_text, int64_t len, int64_t* h_begin
             const uint8_t* q = (const uint8_t*)memchr(p, '>', (size_t)(e - p));
             if (!q) break;
             const int64_t pos = q - h_text;
-            if (pos == 0 || h_text[pos - 1] == '\n') found[(size_t)t].push_back(pos);
+            // a line starts after LF, or after a CR (CRLF, or the lone CR of old Mac files: Python's universal
+            // newlines, which the reference's SeqIO.parse reads with, break lines there too)
+            if (pos == 0 || h_text[pos - 1] == '\n' || h_text[pos - 1] == '\r') found[(size_t)t].push_back(pos);
             p = q + 1;
         }
     };
@@ -157,7 +159,10 @@ int64_t po_fasta_index_host(const uint8_t* h_text, int64_t len, int64_t* h_begin
         for (int64_t pos : found[(size_t)t]) {
             if (prev_begin >= 0 && nrec - 1 < cap && h_end) h_end[nrec - 1] = pos;
             const uint8_t* nl = (const uint8_t*)memchr(h_text + pos, '\n', (size_t)(len - pos));
-            const int64_t b = nl ? (nl - h_text) + 1 : len;
+            int64_t b = nl ? (nl - h_text) + 1 : len;
+            // a CR before that LF which is not its CRLF partner ends the header line earlier
+            const uint8_t* cr = (const uint8_t*)memchr(h_text + pos, '\r', (size_t)(b - pos));
+            if (cr && !(nl && cr + 1 == nl)) b = (cr - h_text) + 1;
             if (nrec < cap && h_begin) h_begin[nrec] = b;
             prev_begin = b;
             ++nrec;

@@ -64,6 +64,23 @@ def fasta_index(text, threads=0):
         cap = int(n)
 
 
+def fasta_header_starts(text, begin, end):
+    """Position of the '>' of every record of `text` (a bytes-like object), given the sequence ranges of
+    fasta_index: a record's header starts where the previous record's range ends; the first one starts
+    after the last line break before its own line."""
+    n = len(begin)
+    starts = np.zeros(n, dtype=np.int64)
+    if n == 0:
+        return starts
+    starts[1:] = np.asarray(end[:-1], dtype=np.int64)
+    raw = bytes(memoryview(text)[: int(begin[0])])
+    j = len(raw)
+    while j > 0 and raw[j - 1] in (10, 13):  # the line break(s) that end the first header line
+        j -= 1
+    starts[0] = max(raw.rfind(b"\n", 0, j), raw.rfind(b"\r", 0, j)) + 1
+    return starts
+
+
 def sequences_to_text(seqs):
     """Pack bare sequences (str/bytes) into one buffer, newline separated, with
     their (begin, end) ranges -- the batch form of the per-sequence worker API."""

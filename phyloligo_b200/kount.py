@@ -56,9 +56,9 @@ class Assembly:
         parts, offsets, lengths = [], np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
         pos = 0
         sep = np.array([10], dtype=np.uint8)
+        starts = engine.fasta_header_starts(text, begin, end)
         for i in range(n):
-            hs = int(end[i - 1]) if i else int(bytes(text[:max(0, int(begin[0]) - 1)]).rfind(b"\n")) + 1
-            header = bytes(text[hs:int(begin[i])])
+            header = bytes(text[int(starts[i]):int(begin[i])])
             fields = header[1:].split()
             self.ids.append(fields[0].decode("latin-1") if fields else "")
             seg = text[int(begin[i]):int(end[i])]

@@ -266,13 +266,13 @@ def write_fastafile(labels_pred, fastafile, outputdir):
     if len(begin) != len(labels_pred):
         raise PhyloligoError("{} holds {} records, the matrix {} rows".format(fastafile, len(begin), len(labels_pred)))
     raw = text.tobytes()
+    starts = engine.fasta_header_starts(raw, begin, end)
     for cl in np.unique(labels_pred):
         name = "data_fasta_unclust.fa" if cl == -1 else "data_fasta_cl{}.fa".format(cl)
         with open(os.path.join(outputdir, name), "wb") as outf:
             for idx in np.where(labels_pred == cl)[0]:
                 b, e = int(begin[idx]), int(end[idx])
-                head0 = raw.rfind(b">", 0, b)
-                title = raw[head0:b].rstrip(b"\r\n")
+                title = raw[int(starts[idx]):b].rstrip(b"\r\n")
                 seq = b"".join(raw[b:e].split())
                 outf.write(title + b"\n")
                 for p in range(0, len(seq), 60):

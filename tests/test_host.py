@@ -234,8 +234,9 @@ def test_savetxt_digits_are_correctly_rounded_everywhere(tmp_path):
 
 
 def test_fasta_index_fuzz_against_the_reader(tmp_path):
-    """Random line soups (headers anywhere, '>' inside lines, blank lines, CRLF, blanks inside lines, no final
-    newline, text before the first header) : po_fasta_index_host yields the records SeqIO.parse would."""
+    """Random line soups (headers anywhere, '>' inside lines, blank lines, CRLF, lone-CR line ends, blanks inside
+    lines, no final newline, text before the first header) : po_fasta_index_host yields the records
+    SeqIO.parse would."""
     from hypothesis import given, settings, strategies as st
 
     line = st.one_of(
@@ -245,7 +246,7 @@ def test_fasta_index_fuzz_against_the_reader(tmp_path):
     path = os.path.join(tmp_path, "fuzz.fa")
 
     @settings(max_examples=300, deadline=None)
-    @given(st.lists(line, min_size=0, max_size=25), st.sampled_from(["\n", "\r\n"]), st.booleans())
+    @given(st.lists(line, min_size=0, max_size=25), st.sampled_from(["\n", "\r\n", "\r"]), st.booleans())
     def run(lines, eol, final_eol):
         text = eol.join(lines) + (eol if final_eol and lines else "")
         raw = text.encode()
@@ -258,3 +259,25 @@ def test_fasta_index_fuzz_against_the_reader(tmp_path):
         assert got == want
 
     run()
+
+
+def test_header_starts_and_per_cluster_fasta(tmp_path):
+    """engine.fasta_header_starts (the '>' of every record, also when a title contains '>' or the file uses CRLF /
+    lone-CR line ends) and phyloselect.write_fastafile on top of it: titles unchanged, sequences wrapped at 60."""
+    from phyloligo_b200 import phyloselect
+
+    for eol in (b"\n", b"\r\n", b"\r"):
+        raw = eol.join([b"junk > before", b">r1 a>b c", b"ACGT" * 20, b"AC", b">r2", b">r3 x", b"TT GG", b""])
+        begin, end = engine.fasta_index(raw)
+        starts = engine.fasta_header_starts(raw, begin, end)
+        titles = [raw[int(s):int(b)].rstrip(b"\r\n") for s, b in zip(starts, begin)]
+        assert titles == [b">r1 a>b c", b">r2", b">r3 x"], (eol, titles)
+        path = os.path.join(tmp_path, "in.fa")
+        with open(path, "wb") as fh:
+            fh.write(raw)
+        out = os.path.join(tmp_path, "out_%d" % len(eol + eol[:1]))
+        os.makedirs(out, exist_ok=True)
+        phyloselect.write_fastafile(np.array([0, 1, 0]), path, out)
+        assert open(os.path.join(out, "data_fasta_cl0.fa"), "rb").read() == \
+            b">r1 a>b c\n" + b"ACGT" * 15 + b"\n" + b"ACGT" * 5 + b"AC\n" + b">r3 x\nTTGG\n"
+        assert open(os.path.join(out, "data_fasta_cl1.fa"), "rb").read() == b">r2\n"
