@@ -328,6 +328,42 @@ def test_host_mirror_repeated_steps_reuse_the_pool():
         assert torch.equal(host, want), seed
 
 
+@pytest.mark.parametrize("metric,n", [("JSD", 1100), ("EuclGram", 900)])
+def test_block_rows_row_panels_and_mirrored_host_sink_one_rank(metric, n):
+    """multigpu.BlockRows on one rank (it owns both block rows): launched whole and in row panels the rows equal
+    the symmetric matrix bit for bit; with MirroredHostSink only the part on and right of the diagonal goes to the
+    host by DMA and the rest is mirrored there (what bench.py's multi-GPU end-to-end leg does on every rank)."""
+    from phyloligo_b200 import multigpu
+
+    rng = np.random.default_rng(n)
+    X = torch.from_numpy(rng.dirichlet(np.ones(256), size=n).astype(np.float32)).cuda()
+    want = engine.distance_matrix_device(X, metric, torch.float32, symmetric=True)
+    P, aux, dim = engine.prepare(X, metric)
+    job = multigpu.BlockRows(n, torch.float32, 0, 1)
+    assert job.rows_owned == n
+    for panel in (None, 256):
+        job.matrix.fill_(float("nan"))
+        job.compute(metric, P, aux, dim, panel_rows=panel)
+        torch.cuda.synchronize()
+        for i in job.my_ranges:
+            a, b = job.ranges[i]
+            assert torch.equal(job.out_rows[i], want[a:b]), (panel, i)
+    host = torch.full((n, n), -1.0, dtype=torch.float32).pin_memory()
+    pool = engine.HostMirror(3)
+    try:
+        sink = multigpu.MirroredHostSink(host, pool)
+        for _ in range(2):  # a sink serves many steps
+            sink.reset()
+            job.compute(metric, P, aux, dim, ship=sink.ship, left_parts=False, panel_rows=256)
+            sink.finish()
+            torch.cuda.synchronize()
+            assert torch.equal(host, want.cpu())
+            assert sink.dma_bytes + sink.mirrored_bytes == n * n * 4 and sink.mirrored_bytes > 0
+    finally:
+        pool.close()
+        job.close()
+
+
 def test_copy2d_strided_views():
     a = torch.arange(40 * 50, dtype=torch.float32, device="cuda").reshape(40, 50)
     h = torch.zeros((40, 50), dtype=torch.float32).pin_memory()
